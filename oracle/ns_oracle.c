@@ -1,0 +1,1182 @@
+/*
+ * ns_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of the per-timestep hot path of
+ * lelecaruso/NavierStokes_Project_NM4PDE (reference tree mounted at /root/reference,
+ * all citations relative to /root/reference/Navier-Stokes):
+ *
+ *   assemble            src/NavierStokes2D.cpp:164-357, src/NavierStokes3D.cpp:163-356,
+ *                       src/Convergence3D.cpp:187-382
+ *   assemble_time_step  src/NavierStokes2D.cpp:361-527, src/NavierStokes3D.cpp:361-544,
+ *                       src/Convergence3D.cpp:391-581
+ *   solve_time_step     src/NavierStokes2D.cpp:530-639 (+3D/CONV twins)
+ *   preconditioners     include/Preconditioners.hpp:118-534 (SIMPLE, aSIMPLE, Yosida, aYosida)
+ *
+ * The arithmetic of the path lives in third-party libraries that are NOT under
+ * /root/reference and not installed here: deal.II (>= 9.3.1, cmake-common.cmake:27-29),
+ * Trilinos (Epetra / EpetraExt / Ifpack through deal.II's TrilinosWrappers).  Their
+ * published algorithms are restated here:
+ *   - FE_SimplexP(2)^dim x FE_SimplexP(1) on affine simplices, FESystem local DoF order
+ *   - MatrixTools::apply_boundary_values (Trilinos path, eliminate_columns=false)
+ *   - SolverGMRES (left preconditioned, 30 tmp vectors, MGS + conditional re-orth.)
+ *   - SolverCG
+ *   - Ifpack_ILU level 0 (inverse diagonal stored, U scaled by it), overlap 0
+ *   - EpetraExt MatrixMatrix::Multiply as used by SparseMatrix::mmult(C, B, V)
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ *  and cannot be built here, so this oracle is pinned only by
+ * pins created in this repo (sympy-exact element matrices, patch tests, convergence
+ * orders; see tests/).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this file.  The product path never does.
+ *
+ * Layout: ONE global CSR over all N = n_u + n_p DoFs (block (1,1) structurally empty,
+ * src/NavierStokes2D.cpp:109-119), rows/cols in the reference's component_wise
+ * numbering (velocity block first, node-interleaved components; then pressure).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NSO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------ */
+/* small helpers                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+static void *xcalloc(size_t n, size_t s)
+{
+  void *p = calloc(n ? n : 1, s);
+  if (!p) { fprintf(stderr, "ns_oracle: out of memory\n"); abort(); }
+  return p;
+}
+
+typedef struct {
+  int n_rows, n_cols;
+  int *rowptr, *colind;
+  double *val;
+} csr_t;
+
+static void csr_free(csr_t *A)
+{
+  free(A->rowptr); free(A->colind); free(A->val);
+  memset(A, 0, sizeof(*A));
+}
+
+static void csr_vmult(const csr_t *A, const double *x, double *y)
+{
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < A->n_rows; ++i) {
+    double s = 0.0;
+    for (int k = A->rowptr[i]; k < A->rowptr[i + 1]; ++k) s += A->val[k] * x[A->colind[k]];
+    y[i] = s;
+  }
+}
+
+static double vdot(int n, const double *a, const double *b)
+{
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+static void vaxpy(int n, double a, const double *x, double *y)
+{
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) y[i] += a * x[i];
+}
+static void vscale(int n, double a, double *x)
+{
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) x[i] *= a;
+}
+static void vcopy(int n, const double *x, double *y) { memcpy(y, x, (size_t)n * sizeof(double)); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Reference-element tables: FE_SimplexP(2) and FE_SimplexP(1)  [deal.II, restated]            */
+/* Barycentrics l0 = 1 - sum(x), lk = x_{k-1}.  P2: vertex l(2l-1); edge 4 la lb with edges    */
+/* (0,1),(1,2),(2,0),(0,3),(1,3),(2,3).  ("Local DoF order")              */
+/* ------------------------------------------------------------------------------------------ */
+static const int EDGE_A[6] = {0, 1, 2, 0, 1, 2};
+static const int EDGE_B[6] = {1, 2, 0, 3, 3, 3};
+
+static void bary(int dim, const double *x, double *l, double gl[4][3])
+{
+  double s = 0;
+  for (int d = 0; d < dim; ++d) s += x[d];
+  l[0] = 1.0 - s;
+  for (int d = 0; d < dim; ++d) l[d + 1] = x[d];
+  for (int v = 0; v <= dim; ++v)
+    for (int d = 0; d < dim; ++d) gl[v][d] = (v == 0) ? -1.0 : (v - 1 == d ? 1.0 : 0.0);
+}
+
+/* phi2[a*nq+q], dphi2[(a*nq+q)*dim+d], psi[v*nq+q], dpsi[(v*nq+q)*dim+d] */
+NSO_API void nso_tabulate(int dim, int nq, const double *xi, double *phi2, double *dphi2, double *psi,
+                          double *dpsi)
+{
+  const int nv = dim + 1, ne = (dim == 2) ? 3 : 6;
+  for (int q = 0; q < nq; ++q) {
+    double l[4], gl[4][3];
+    bary(dim, xi + (size_t)q * dim, l, gl);
+    for (int v = 0; v < nv; ++v) {
+      phi2[v * nq + q] = l[v] * (2.0 * l[v] - 1.0);
+      for (int d = 0; d < dim; ++d) dphi2[((size_t)v * nq + q) * dim + d] = (4.0 * l[v] - 1.0) * gl[v][d];
+      psi[v * nq + q] = l[v];
+      if (dpsi)
+        for (int d = 0; d < dim; ++d) dpsi[((size_t)v * nq + q) * dim + d] = gl[v][d];
+    }
+    for (int e = 0; e < ne; ++e) {
+      const int a = EDGE_A[e], b = EDGE_B[e], idx = nv + e;
+      phi2[idx * nq + q] = 4.0 * l[a] * l[b];
+      for (int d = 0; d < dim; ++d)
+        dphi2[((size_t)idx * nq + q) * dim + d] = 4.0 * (l[b] * gl[a][d] + l[a] * gl[b][d]);
+    }
+  }
+}
+
+/* FESystem(P2^dim, P1) local DoF i -> component (0..dim-1 velocity, dim pressure) and the      */
+/* index of the scalar base function (P2 node 0..n2-1 or P1 vertex).                           */
+static void local_dof(int dim, int i, int *comp, int *base)
+{
+  const int nv = dim + 1, per_v = dim + 1;
+  if (i < nv * per_v) {
+    *comp = i % per_v;
+    *base = i / per_v;
+  } else {
+    const int r = i - nv * per_v;
+    *comp = r % dim;
+    *base = nv + r / dim;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  csr_t L, U;      /* strictly lower (unit diag implied), strictly upper scaled by dinv */
+  double *dinv;
+  int n;
+} ilu_t;
+
+typedef struct nso_ctx {
+  int dim, variant; /* 0 = NavierStokes2D, 1 = NavierStokes3D, 2 = Convergence3D */
+  int nc, N, nu, np, dpc, n2, nq;
+  double *vcoords;
+  int *cell_dofs;
+  double *xi, *w, *phi2, *dphi2, *psi;
+  int *rowptr, *colind;
+  int nnz;
+  double *sys, *mass, *stiff, *conv; /* BlockSparseMatrix x4 on the shared pattern */
+  /* pressure mass on its own p-p pattern (src/NavierStokes2D.cpp:127-142) */
+  int *pm_rowptr, *pm_colind;
+  double *pm_val;
+  double *rhs, *sol, *sol_owned, *prev_sol;
+  int nbc;
+  int *bc_rows;
+  double *bc_vals;
+  double *neumann; /* per-step face-integral contribution to rhs (CONV), length N, may be NULL */
+  double visc, dt;
+  int dirichlet_mode; /* 0: keep nonzero diagonal, rhs = g*a_ii (deal.II Trilinos path); 1: replace by dbar */
+  int *part;          /* DoF -> subdomain (block-Jacobi ILU like mpirun -n P), NULL = 1 part */
+  /* solver settings */
+  int gmres_tmp;            /* max_n_tmp_vectors, deal.II default 30 */
+  double outer_tol;         /* 1e-4 absolute (src/NavierStokes2D.cpp:535) */
+  int outer_maxit;
+  double inner_rtol;        /* 1e-2 (Preconditioners.hpp:260) */
+  int inner_maxit;
+  double alpha_simple, alpha_asimple;
+  /* per-solve views */
+  csr_t F, B, Bt, S;
+  double *D, *Dinv, *negDinv;
+  ilu_t iluF, iluS;
+  /* statistics of the last solve */
+  long n_inner_F, n_inner_S, n_F_solves, n_S_solves, n_vmult;
+  double *res_hist;
+  int n_res_hist, cap_res_hist;
+} nso_ctx;
+
+NSO_API nso_ctx *nso_create(int dim, int variant, int nc, const double *vcoords, const int *cell_dofs, int N,
+                            int nu, const int *rowptr, const int *colind, int nq, const double *xi,
+                            const double *w, double visc, double dt)
+{
+  nso_ctx *c = (nso_ctx *)xcalloc(1, sizeof(nso_ctx));
+  c->dim = dim; c->variant = variant; c->nc = nc; c->N = N; c->nu = nu; c->np = N - nu;
+  c->n2 = (dim == 2) ? 6 : 10;
+  c->dpc = dim * c->n2 + dim + 1;
+  c->nq = nq;
+  c->visc = visc; c->dt = dt;
+  size_t ncoord = (size_t)nc * (dim + 1) * dim;
+  c->vcoords = (double *)xcalloc(ncoord, sizeof(double));
+  memcpy(c->vcoords, vcoords, ncoord * sizeof(double));
+  c->cell_dofs = (int *)xcalloc((size_t)nc * c->dpc, sizeof(int));
+  memcpy(c->cell_dofs, cell_dofs, (size_t)nc * c->dpc * sizeof(int));
+  c->xi = (double *)xcalloc((size_t)nq * dim, sizeof(double));
+  memcpy(c->xi, xi, (size_t)nq * dim * sizeof(double));
+  c->w = (double *)xcalloc(nq, sizeof(double));
+  memcpy(c->w, w, (size_t)nq * sizeof(double));
+  c->phi2 = (double *)xcalloc((size_t)c->n2 * nq, sizeof(double));
+  c->dphi2 = (double *)xcalloc((size_t)c->n2 * nq * dim, sizeof(double));
+  c->psi = (double *)xcalloc((size_t)(dim + 1) * nq, sizeof(double));
+  nso_tabulate(dim, nq, xi, c->phi2, c->dphi2, c->psi, NULL);
+  c->rowptr = (int *)xcalloc((size_t)N + 1, sizeof(int));
+  memcpy(c->rowptr, rowptr, ((size_t)N + 1) * sizeof(int));
+  c->nnz = rowptr[N];
+  c->colind = (int *)xcalloc(c->nnz, sizeof(int));
+  memcpy(c->colind, colind, (size_t)c->nnz * sizeof(int));
+  c->sys = (double *)xcalloc(c->nnz, sizeof(double));
+  c->mass = (double *)xcalloc(c->nnz, sizeof(double));
+  c->stiff = (double *)xcalloc(c->nnz, sizeof(double));
+  c->conv = (double *)xcalloc(c->nnz, sizeof(double));
+  c->rhs = (double *)xcalloc(N, sizeof(double));
+  c->sol = (double *)xcalloc(N, sizeof(double));
+  c->sol_owned = (double *)xcalloc(N, sizeof(double));
+  c->prev_sol = (double *)xcalloc(N, sizeof(double));
+  c->gmres_tmp = 30;
+  c->outer_tol = 1e-4;
+  c->outer_maxit = 100000;
+  c->inner_rtol = 1e-2;
+  c->inner_maxit = 10000;
+  c->alpha_simple = 0.5;  /* Preconditioners.hpp:207 */
+  c->alpha_asimple = 1.0; /* Preconditioners.hpp:328 */
+  return c;
+}
+
+static void ilu_free(ilu_t *f)
+{
+  csr_free(&f->L); csr_free(&f->U); free(f->dinv);
+  memset(f, 0, sizeof(*f));
+}
+
+static void free_solve_views(nso_ctx *c)
+{
+  csr_free(&c->F); csr_free(&c->B); csr_free(&c->Bt); csr_free(&c->S);
+  free(c->D); free(c->Dinv); free(c->negDinv);
+  c->D = c->Dinv = c->negDinv = NULL;
+  ilu_free(&c->iluF); ilu_free(&c->iluS);
+}
+
+NSO_API void nso_destroy(nso_ctx *c)
+{
+  if (!c) return;
+  free_solve_views(c);
+  free(c->vcoords); free(c->cell_dofs); free(c->xi); free(c->w); free(c->phi2); free(c->dphi2); free(c->psi);
+  free(c->rowptr); free(c->colind); free(c->sys); free(c->mass); free(c->stiff); free(c->conv);
+  free(c->pm_rowptr); free(c->pm_colind); free(c->pm_val);
+  free(c->rhs); free(c->sol); free(c->sol_owned); free(c->prev_sol);
+  free(c->bc_rows); free(c->bc_vals); free(c->neumann); free(c->part); free(c->res_hist);
+  free(c);
+}
+
+NSO_API void nso_set_pressure_mass_pattern(nso_ctx *c, const int *rowptr, const int *colind)
+{
+  free(c->pm_rowptr); free(c->pm_colind); free(c->pm_val);
+  c->pm_rowptr = (int *)xcalloc((size_t)c->np + 1, sizeof(int));
+  memcpy(c->pm_rowptr, rowptr, ((size_t)c->np + 1) * sizeof(int));
+  int nnz = rowptr[c->np];
+  c->pm_colind = (int *)xcalloc(nnz, sizeof(int));
+  memcpy(c->pm_colind, colind, (size_t)nnz * sizeof(int));
+  c->pm_val = (double *)xcalloc(nnz, sizeof(double));
+}
+
+NSO_API void nso_set_dirichlet(nso_ctx *c, int n, const int *rows, const double *vals)
+{
+  free(c->bc_rows); free(c->bc_vals);
+  c->nbc = n;
+  c->bc_rows = (int *)xcalloc(n, sizeof(int));
+  c->bc_vals = (double *)xcalloc(n, sizeof(double));
+  memcpy(c->bc_rows, rows, (size_t)n * sizeof(int));
+  memcpy(c->bc_vals, vals, (size_t)n * sizeof(double));
+}
+NSO_API void nso_set_dirichlet_values(nso_ctx *c, const double *vals)
+{
+  memcpy(c->bc_vals, vals, (size_t)c->nbc * sizeof(double));
+}
+NSO_API void nso_set_neumann_rhs(nso_ctx *c, const double *add)
+{
+  if (!add) { free(c->neumann); c->neumann = NULL; return; }
+  if (!c->neumann) c->neumann = (double *)xcalloc(c->N, sizeof(double));
+  memcpy(c->neumann, add, (size_t)c->N * sizeof(double));
+}
+NSO_API void nso_set_solution(nso_ctx *c, const double *x)
+{ /* VectorTools::interpolate -> solution_owned; solution = solution_owned (NavierStokes2D.cpp:708-709) */
+  memcpy(c->sol_owned, x, (size_t)c->N * sizeof(double));
+  memcpy(c->sol, x, (size_t)c->N * sizeof(double));
+}
+NSO_API void nso_set_partition(nso_ctx *c, const int *part)
+{
+  free(c->part); c->part = NULL;
+  if (part) {
+    c->part = (int *)xcalloc(c->N, sizeof(int));
+    memcpy(c->part, part, (size_t)c->N * sizeof(int));
+  }
+}
+NSO_API void nso_set_options(nso_ctx *c, int dirichlet_mode, int gmres_tmp, double outer_tol, int outer_maxit,
+                             double inner_rtol, int inner_maxit)
+{
+  c->dirichlet_mode = dirichlet_mode;
+  if (gmres_tmp > 2) c->gmres_tmp = gmres_tmp;
+  if (outer_tol > 0) c->outer_tol = outer_tol;
+  if (outer_maxit > 0) c->outer_maxit = outer_maxit;
+  if (inner_rtol > 0) c->inner_rtol = inner_rtol;
+  if (inner_maxit > 0) c->inner_maxit = inner_maxit;
+}
+
+NSO_API double *nso_ptr(nso_ctx *c, const char *name)
+{
+  if (!strcmp(name, "sys")) return c->sys;
+  if (!strcmp(name, "mass")) return c->mass;
+  if (!strcmp(name, "stiff")) return c->stiff;
+  if (!strcmp(name, "conv")) return c->conv;
+  if (!strcmp(name, "pmass")) return c->pm_val;
+  if (!strcmp(name, "rhs")) return c->rhs;
+  if (!strcmp(name, "sol")) return c->sol;
+  if (!strcmp(name, "sol_owned")) return c->sol_owned;
+  if (!strcmp(name, "S_val")) return c->S.val;
+  if (!strcmp(name, "res_hist")) return c->res_hist;
+  return NULL;
+}
+NSO_API int *nso_iptr(nso_ctx *c, const char *name)
+{
+  if (!strcmp(name, "S_rowptr")) return c->S.rowptr;
+  if (!strcmp(name, "S_colind")) return c->S.colind;
+  return NULL;
+}
+NSO_API long nso_stat(nso_ctx *c, const char *name)
+{
+  if (!strcmp(name, "n_inner_F")) return c->n_inner_F;
+  if (!strcmp(name, "n_inner_S")) return c->n_inner_S;
+  if (!strcmp(name, "n_F_solves")) return c->n_F_solves;
+  if (!strcmp(name, "n_S_solves")) return c->n_S_solves;
+  if (!strcmp(name, "n_vmult")) return c->n_vmult;
+  if (!strcmp(name, "S_nnz")) return c->S.rowptr ? c->S.rowptr[c->S.n_rows] : 0;
+  if (!strcmp(name, "n_res_hist")) return c->n_res_hist;
+  return -1;
+}
+
+/* position of (row, col) in the shared pattern; columns sorted ascending */
+static inline int find_pos(const int *rowptr, const int *colind, int row, int col)
+{
+  int lo = rowptr[row], hi = rowptr[row + 1] - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    int cm = colind[mid];
+    if (cm == col) return mid;
+    if (cm < col) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FEValues::reinit for an affine simplex [deal.II, restated]: J = [x1-x0, ...], detJ, J^{-1}   */
+/* ------------------------------------------------------------------------------------------ */
+static double affine_map(int dim, const double *vc, double Jinv[3][3])
+{
+  double J[3][3];
+  for (int r = 0; r < dim; ++r)
+    for (int k = 0; k < dim; ++k) J[r][k] = vc[(k + 1) * dim + r] - vc[r];
+  double det;
+  if (dim == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double id = 1.0 / det;
+    Jinv[0][0] = J[1][1] * id;  Jinv[0][1] = -J[0][1] * id;
+    Jinv[1][0] = -J[1][0] * id; Jinv[1][1] = J[0][0] * id;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double id = 1.0 / det;
+    Jinv[0][0] = c00 * id;
+    Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Jinv[1][0] = c01 * id;
+    Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Jinv[2][0] = c02 * id;
+    Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  }
+  return det;
+}
+
+/* Per cell, per q: scalar value and physical gradient of every local DoF's shape function.   */
+/* val[i], grad[i][d] for the single nonzero component comp[i] of DoF i.                      */
+typedef struct {
+  int comp[34], base[34];
+} ldof_t;
+
+static void fill_ldof(int dim, int dpc, ldof_t *ld)
+{
+  for (int i = 0; i < dpc; ++i) local_dof(dim, i, &ld->comp[i], &ld->base[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cell loop shared by assemble() and assemble_time_step()                                    */
+/* first = 1: NavierStokes::assemble (5 local matrices + rhs); first = 0: assemble_time_step  */
+/* ------------------------------------------------------------------------------------------ */
+static void cell_loop(nso_ctx *c, int first)
+{
+  const int dim = c->dim, dpc = c->dpc, nq = c->nq, n2 = c->n2;
+  ldof_t ld;
+  fill_ldof(dim, dpc, &ld);
+  /* which terms the variant has in this loop */
+  const int temam = first ? 1 : (c->variant == 1 ? 0 : 1);           /* NavierStokes3D.cpp:456 has no Temam */
+  const int conv_mult = (first && c->variant == 2) ? 2 : 1;          /* Convergence3D.cpp:277 and :284 */
+
+#pragma omp parallel
+  {
+    double *cm = (double *)xcalloc((size_t)dpc * dpc, sizeof(double));   /* cell_matrix (B blocks) */
+    double *cmass = (double *)xcalloc((size_t)dpc * dpc, sizeof(double));
+    double *cstiff = (double *)xcalloc((size_t)dpc * dpc, sizeof(double));
+    double *cconv = (double *)xcalloc((size_t)dpc * dpc, sizeof(double));
+    double *cpm = (double *)xcalloc((size_t)dpc * dpc, sizeof(double));
+    double crhs[34];
+    double val[34], grad[34][3], divi[34];
+#pragma omp for schedule(static)
+    for (int cell = 0; cell < c->nc; ++cell) {
+      const double *vc = c->vcoords + (size_t)cell * (dim + 1) * dim;
+      const int *dofs = c->cell_dofs + (size_t)cell * dpc;
+      double Jinv[3][3];
+      const double det = affine_map(dim, vc, Jinv);
+      memset(cm, 0, sizeof(double) * dpc * dpc);
+      memset(cmass, 0, sizeof(double) * dpc * dpc);
+      memset(cstiff, 0, sizeof(double) * dpc * dpc);
+      memset(cconv, 0, sizeof(double) * dpc * dpc);
+      memset(cpm, 0, sizeof(double) * dpc * dpc);
+      memset(crhs, 0, sizeof(crhs));
+      for (int q = 0; q < nq; ++q) {
+        const double JxW = det * c->w[q];
+        /* shape values / gradients of all local DoFs at q */
+        for (int i = 0; i < dpc; ++i) {
+          const int b = ld.base[i];
+          if (ld.comp[i] < dim) {
+            val[i] = c->phi2[b * nq + q];
+            const double *gh = c->dphi2 + ((size_t)b * nq + q) * dim;
+            for (int d = 0; d < dim; ++d) {
+              double s = 0.0; /* grad = J^{-T} grad_hat */
+              for (int k = 0; k < dim; ++k) s += Jinv[k][d] * gh[k];
+              grad[i][d] = s;
+            }
+            divi[i] = grad[i][ld.comp[i]];
+          } else {
+            val[i] = c->psi[b * nq + q];
+            divi[i] = 0.0;
+          }
+        }
+        /* get_function_values / get_function_divergences(solution) (NavierStokes2D.cpp:225-229,430-434) */
+        double u[3] = {0, 0, 0}, divu = 0.0;
+        for (int i = 0; i < dpc; ++i)
+          if (ld.comp[i] < dim) {
+            const double U = c->sol[dofs[i]];
+            u[ld.comp[i]] += U * val[i];
+            divu += U * divi[i];
+          }
+        for (int i = 0; i < dpc; ++i) {
+          const int ci = ld.comp[i];
+          for (int j = 0; j < dpc; ++j) {
+            const int cj = ld.comp[j];
+            const size_t ij = (size_t)i * dpc + j;
+            if (ci < dim && cj < dim && ci == cj) {
+              double gg = 0.0, adv = 0.0;
+              for (int d = 0; d < dim; ++d) { gg += grad[i][d] * grad[j][d]; adv += grad[j][d] * u[d]; }
+              const double vv = val[i] * val[j];
+              if (first) {
+                cstiff[ij] += c->visc * gg * JxW;          /* :247 */
+                cmass[ij] += vv / c->dt * JxW;             /* :250 */
+              }
+              for (int m = 0; m < conv_mult; ++m) cconv[ij] += adv * val[i] * JxW; /* :253 / :444 */
+              if (temam) cconv[ij] += 0.5 * divu * vv * JxW;                      /* :256 / :446 */
+            }
+            if (first) {
+              if (ci < dim && cj == dim) cm[ij] -= val[j] * divi[i] * JxW; /* :259 */
+              if (ci == dim && cj < dim) cm[ij] += val[i] * divi[j] * JxW; /* :262 */
+              if (ci == dim && cj == dim) cpm[ij] += val[i] * val[j] / c->visc * JxW; /* :265 */
+            }
+          }
+          if (ci < dim) crhs[i] += u[ci] * val[i] * JxW / c->dt; /* :270 / :450 */
+        }
+      }
+      /* scatter (NavierStokes2D.cpp:305-312 / 485-487) */
+      for (int i = 0; i < dpc; ++i) {
+        const int gi = dofs[i];
+        for (int j = 0; j < dpc; ++j) {
+          const int gj = dofs[j];
+          const size_t ij = (size_t)i * dpc + j;
+          const int both_p = (ld.comp[i] == dim && ld.comp[j] == dim);
+          if (!both_p) {
+            const int pos = find_pos(c->rowptr, c->colind, gi, gj);
+            if (pos < 0) { fprintf(stderr, "ns_oracle: pattern miss (%d,%d)\n", gi, gj); abort(); }
+            if (first) {
+#pragma omp atomic
+              c->sys[pos] += cm[ij];
+#pragma omp atomic
+              c->mass[pos] += cmass[ij];
+#pragma omp atomic
+              c->stiff[pos] += cstiff[ij];
+            }
+#pragma omp atomic
+            c->conv[pos] += cconv[ij];
+          } else if (first && c->pm_rowptr) {
+            const int pos = find_pos(c->pm_rowptr, c->pm_colind, gi - c->nu, gj - c->nu);
+            if (pos >= 0) {
+#pragma omp atomic
+              c->pm_val[pos] += cpm[ij];
+            }
+          }
+        }
+#pragma omp atomic
+        c->rhs[gi] += crhs[i];
+      }
+    }
+    free(cm); free(cmass); free(cstiff); free(cconv); free(cpm);
+  }
+  (void)n2;
+}
+
+/* MatrixTools::apply_boundary_values(bv, system_matrix, solution, system_rhs, false)          */
+/* [deal.II matrix_tools_once.cc, Trilinos block path, restated; NavierStokes2D.cpp:354,524]   */
+static void apply_dirichlet(nso_ctx *c)
+{
+  if (c->nbc == 0) return;
+  const int nu = c->nu;
+  /* first nonzero diagonal entry of block (0,0) in the local range */
+  double dbar = 1.0;
+  for (int i = 0; i < nu; ++i) {
+    const int p = find_pos(c->rowptr, c->colind, i, i);
+    if (p >= 0 && c->sys[p] != 0.0) { dbar = fabs(c->sys[p]); break; }
+  }
+  for (int k = 0; k < c->nbc; ++k) {
+    const int r = c->bc_rows[k];
+    if (r >= nu) continue; /* only velocity DoFs are ever constrained (ComponentMask) */
+    double diag = 0.0;
+    for (int p = c->rowptr[r]; p < c->rowptr[r + 1]; ++p) {
+      const int col = c->colind[p];
+      if (col == r) {
+        /* SparseMatrix::clear_row keeps a nonzero diagonal; mode 1 replaces it */
+        if (c->dirichlet_mode == 1 || c->sys[p] == 0.0) c->sys[p] = dbar;
+        diag = c->sys[p];
+      } else
+        c->sys[p] = 0.0; /* block (0,0) off-diagonals and the whole row of block (0,1) */
+    }
+    c->sol[r] = c->bc_vals[k];
+    c->rhs[r] = c->bc_vals[k] * diag;
+  }
+}
+
+/* NavierStokes::assemble (first step) */
+NSO_API void nso_assemble_first(nso_ctx *c)
+{
+  memset(c->sys, 0, sizeof(double) * c->nnz);
+  memset(c->mass, 0, sizeof(double) * c->nnz);
+  memset(c->stiff, 0, sizeof(double) * c->nnz);
+  memset(c->conv, 0, sizeof(double) * c->nnz);
+  memset(c->rhs, 0, sizeof(double) * c->N);
+  if (c->pm_val) memset(c->pm_val, 0, sizeof(double) * c->pm_rowptr[c->np]);
+  cell_loop(c, 1);
+  if (c->neumann) vaxpy(c->N, 1.0, c->neumann, c->rhs); /* Convergence3D.cpp:309-330 */
+  /* system_matrix.add(1, mass); add(1, convection); add(1, stiffness)  (:323-325) */
+  for (int k = 0; k < c->nnz; ++k) c->sys[k] += c->mass[k];
+  for (int k = 0; k < c->nnz; ++k) c->sys[k] += c->conv[k];
+  for (int k = 0; k < c->nnz; ++k) c->sys[k] += c->stiff[k];
+  apply_dirichlet(c);
+}
+
+/* NavierStokes::assemble_time_step */
+NSO_API void nso_assemble_step(nso_ctx *c)
+{
+  for (int k = 0; k < c->nnz; ++k) c->sys[k] += -1.0 * c->conv[k]; /* :388 */
+  memset(c->conv, 0, sizeof(double) * c->nnz);
+  memset(c->rhs, 0, sizeof(double) * c->N);
+  cell_loop(c, 0);
+  if (c->neumann) vaxpy(c->N, 1.0, c->neumann, c->rhs); /* Convergence3D.cpp:503-527 */
+  for (int k = 0; k < c->nnz; ++k) c->sys[k] += c->conv[k]; /* :492 */
+  apply_dirichlet(c);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* block views                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+static void extract_block(const nso_ctx *c, const double *val, int r0, int r1, int c0, int c1, csr_t *out)
+{
+  out->n_rows = r1 - r0;
+  out->n_cols = c1 - c0;
+  out->rowptr = (int *)xcalloc((size_t)out->n_rows + 1, sizeof(int));
+  for (int i = r0; i < r1; ++i) {
+    int cnt = 0;
+    for (int p = c->rowptr[i]; p < c->rowptr[i + 1]; ++p)
+      if (c->colind[p] >= c0 && c->colind[p] < c1) ++cnt;
+    out->rowptr[i - r0 + 1] = out->rowptr[i - r0] + cnt;
+  }
+  const int nnz = out->rowptr[out->n_rows];
+  out->colind = (int *)xcalloc(nnz, sizeof(int));
+  out->val = (double *)xcalloc(nnz, sizeof(double));
+  for (int i = r0; i < r1; ++i) {
+    int o = out->rowptr[i - r0];
+    for (int p = c->rowptr[i]; p < c->rowptr[i + 1]; ++p)
+      if (c->colind[p] >= c0 && c->colind[p] < c1) {
+        out->colind[o] = c->colind[p] - c0;
+        out->val[o] = val[p];
+        ++o;
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Ifpack_ILU, level of fill 0, overlap 0 [Ifpack_ILU.cpp Compute()/ApplyInverse(), restated]  */
+/* ------------------------------------------------------------------------------------------ */
+static void ilu_factor(const csr_t *A, const int *part, ilu_t *f)
+{
+  const int n = A->n_rows;
+  f->n = n;
+  f->L.n_rows = f->U.n_rows = n;
+  f->L.n_cols = f->U.n_cols = n;
+  f->L.rowptr = (int *)xcalloc((size_t)n + 1, sizeof(int));
+  f->U.rowptr = (int *)xcalloc((size_t)n + 1, sizeof(int));
+  f->dinv = (double *)xcalloc(n, sizeof(double));
+  for (int i = 0; i < n; ++i) {
+    int nl = 0, nuu = 0;
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p) {
+      const int j = A->colind[p];
+      if (part && part[j] != part[i]) continue; /* Ifpack_LocalFilter: drop off-process columns */
+      if (j < i) ++nl; else if (j > i) ++nuu;
+    }
+    f->L.rowptr[i + 1] = f->L.rowptr[i] + nl;
+    f->U.rowptr[i + 1] = f->U.rowptr[i] + nuu;
+  }
+  f->L.colind = (int *)xcalloc(f->L.rowptr[n], sizeof(int));
+  f->L.val = (double *)xcalloc(f->L.rowptr[n], sizeof(double));
+  f->U.colind = (int *)xcalloc(f->U.rowptr[n], sizeof(int));
+  f->U.val = (double *)xcalloc(f->U.rowptr[n], sizeof(double));
+  for (int i = 0; i < n; ++i) { /* InitValues */
+    int ol = f->L.rowptr[i], ou = f->U.rowptr[i];
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p) {
+      const int j = A->colind[p];
+      if (part && part[j] != part[i]) continue;
+      if (j < i) { f->L.colind[ol] = j; f->L.val[ol++] = A->val[p]; }
+      else if (j > i) { f->U.colind[ou] = j; f->U.val[ou++] = A->val[p]; }
+      else f->dinv[i] = A->val[p];
+    }
+  }
+  /* Compute(): rows in natural local order; rows of different parts never interact */
+  int *colflag = (int *)xcalloc(n, sizeof(int));
+  for (int j = 0; j < n; ++j) colflag[j] = -1;
+  int maxrow = 0;
+  for (int i = 0; i < n; ++i) {
+    int len = (f->L.rowptr[i + 1] - f->L.rowptr[i]) + (f->U.rowptr[i + 1] - f->U.rowptr[i]) + 1;
+    if (len > maxrow) maxrow = len;
+  }
+  int *InI = (int *)xcalloc((size_t)maxrow + 1, sizeof(int));
+  double *InV = (double *)xcalloc((size_t)maxrow + 1, sizeof(double));
+  const double MinDiag = 2.2250738585072014e-308, MaxDiag = 1.0 / MinDiag;
+  for (int i = 0; i < n; ++i) {
+    const int NumL = f->L.rowptr[i + 1] - f->L.rowptr[i];
+    const int NumU = f->U.rowptr[i + 1] - f->U.rowptr[i];
+    for (int k = 0; k < NumL; ++k) { InI[k] = f->L.colind[f->L.rowptr[i] + k]; InV[k] = f->L.val[f->L.rowptr[i] + k]; }
+    InV[NumL] = f->dinv[i]; InI[NumL] = i;
+    for (int k = 0; k < NumU; ++k) { InI[NumL + 1 + k] = f->U.colind[f->U.rowptr[i] + k]; InV[NumL + 1 + k] = f->U.val[f->U.rowptr[i] + k]; }
+    const int NumIn = NumL + NumU + 1;
+    for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = k;
+    for (int jj = 0; jj < NumL; ++jj) {
+      const int j = InI[jj];
+      const double multiplier = InV[jj];
+      InV[jj] *= f->dinv[j];
+      for (int k = f->U.rowptr[j]; k < f->U.rowptr[j + 1]; ++k) {
+        const int kk = colflag[f->U.colind[k]];
+        if (kk > -1) InV[kk] -= multiplier * f->U.val[k];
+      }
+    }
+    for (int k = 0; k < NumL; ++k) f->L.val[f->L.rowptr[i] + k] = InV[k];
+    double d = InV[NumL];
+    if (fabs(d) > MaxDiag) d = (d < 0) ? -MinDiag : MinDiag; else d = 1.0 / d;
+    f->dinv[i] = d;
+    for (int k = 0; k < NumU; ++k) f->U.val[f->U.rowptr[i] + k] = InV[NumL + 1 + k] * d;
+    for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = -1;
+  }
+  free(colflag); free(InI); free(InV);
+}
+
+/* y = U^{-1} D^{-1} L^{-1} x  (Ifpack_ILU::Solve) */
+static void ilu_apply(void *vf, const double *x, double *y)
+{
+  const ilu_t *f = (const ilu_t *)vf;
+  const int n = f->n;
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int k = f->L.rowptr[i]; k < f->L.rowptr[i + 1]; ++k) s += f->L.val[k] * y[f->L.colind[k]];
+    y[i] = x[i] - s;
+  }
+  for (int i = 0; i < n; ++i) y[i] *= f->dinv[i];
+  for (int i = n - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int k = f->U.rowptr[i]; k < f->U.rowptr[i + 1]; ++k) s += f->U.val[k] * y[f->U.colind[k]];
+    y[i] = y[i] - s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* SparseMatrix::mmult(C, B, V): C = A * diag(V) * B  [deal.II + EpetraExt, restated]          */
+/* ------------------------------------------------------------------------------------------ */
+static void csr_mmult_diag(const csr_t *A, const double *V, const csr_t *Bm, csr_t *C)
+{
+  const int n = A->n_rows, m = Bm->n_cols;
+  C->n_rows = n; C->n_cols = m;
+  C->rowptr = (int *)xcalloc((size_t)n + 1, sizeof(int));
+  int *mark = (int *)xcalloc(m, sizeof(int));
+  for (int j = 0; j < m; ++j) mark[j] = -1;
+  for (int i = 0; i < n; ++i) { /* symbolic */
+    int cnt = 0;
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p) {
+      const int k = A->colind[p];
+      for (int r = Bm->rowptr[k]; r < Bm->rowptr[k + 1]; ++r)
+        if (mark[Bm->colind[r]] != i) { mark[Bm->colind[r]] = i; ++cnt; }
+    }
+    C->rowptr[i + 1] = C->rowptr[i] + cnt;
+  }
+  const int nnz = C->rowptr[n];
+  C->colind = (int *)xcalloc(nnz, sizeof(int));
+  C->val = (double *)xcalloc(nnz, sizeof(double));
+  for (int j = 0; j < m; ++j) mark[j] = -1;
+  double *acc = (double *)xcalloc(m, sizeof(double));
+  for (int i = 0; i < n; ++i) {
+    int o = C->rowptr[i];
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p) {
+      const int k = A->colind[p];
+      for (int r = Bm->rowptr[k]; r < Bm->rowptr[k + 1]; ++r) {
+        const int j = Bm->colind[r];
+        if (mark[j] != i) { mark[j] = i; C->colind[o++] = j; acc[j] = 0.0; }
+      }
+    }
+    /* sort the row's columns ascending (Epetra stores sorted local column ids) */
+    int *cols = C->colind + C->rowptr[i];
+    const int len = C->rowptr[i + 1] - C->rowptr[i];
+    for (int a = 1; a < len; ++a) {
+      int key = cols[a], b = a - 1;
+      while (b >= 0 && cols[b] > key) { cols[b + 1] = cols[b]; --b; }
+      cols[b + 1] = key;
+    }
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p) {
+      const int k = A->colind[p];
+      const double a = A->val[p] * V[k]; /* mod_B: left matrix columns scaled by V */
+      for (int r = Bm->rowptr[k]; r < Bm->rowptr[k + 1]; ++r) acc[Bm->colind[r]] += a * Bm->val[r];
+    }
+    for (int a = 0; a < len; ++a) C->val[C->rowptr[i] + a] = acc[cols[a]];
+  }
+  free(mark); free(acc);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Krylov solvers [deal.II SolverGMRES / SolverCG, restated]                                  */
+/* ------------------------------------------------------------------------------------------ */
+typedef void (*op_fn)(void *ctx, const double *x, double *y);
+
+typedef struct {
+  int maxit;
+  double tol;
+  int last_step;
+  double last_value;
+  int ok;
+  /* optional residual history (SolverControl log_history) */
+  nso_ctx *hist;
+  /* block split for BlockVector reductions (nb = 0: plain vector) */
+  int nb;
+} control_t;
+
+static void hist_push(nso_ctx *c, double r)
+{
+  if (!c) return;
+  if (c->n_res_hist == c->cap_res_hist) {
+    c->cap_res_hist = c->cap_res_hist ? 2 * c->cap_res_hist : 256;
+    c->res_hist = (double *)realloc(c->res_hist, sizeof(double) * c->cap_res_hist);
+  }
+  c->res_hist[c->n_res_hist++] = r;
+}
+
+/* SolverControl::check: 0 iterate, 1 success, 2 failure */
+static int control_check(control_t *ctl, int step, double value)
+{
+  ctl->last_step = step;
+  ctl->last_value = value;
+  hist_push(ctl->hist, value);
+  if (value <= ctl->tol) { ctl->ok = 1; return 1; }
+  if (step >= ctl->maxit || isnan(value)) { ctl->ok = 0; return 2; }
+  return 0;
+}
+
+/* BlockVector::operator* adds the per-block dot products */
+static double bdot(int n, int nb, const double *a, const double *b)
+{
+  if (nb <= 0 || nb >= n) return vdot(n, a, b);
+  return vdot(nb, a, b) + vdot(n - nb, a + nb, b + nb);
+}
+
+static void givens_rotation(double *h, double *b, double *ci, double *si, int col)
+{
+  for (int i = 0; i < col; ++i) {
+    const double s = si[i], cc = ci[i], dummy = h[i];
+    h[i] = cc * dummy + s * h[i + 1];
+    h[i + 1] = -s * dummy + cc * h[i + 1];
+  }
+  const double r = 1.0 / sqrt(h[col] * h[col] + h[col + 1] * h[col + 1]);
+  si[col] = h[col + 1] * r;
+  ci[col] = h[col] * r;
+  h[col] = ci[col] * h[col] + si[col] * h[col + 1];
+  b[col + 1] = -si[col] * b[col];
+  b[col] *= ci[col];
+}
+
+/* SolverGMRES::solve, left preconditioning, default (preconditioned) residual.               */
+/* V: (n_tmp) work vectors of length n.                                                       */
+static int gmres_solve(int n, op_fn A, void *Actx, op_fn P, void *Pctx, double *x, const double *b, int n_tmp,
+                       control_t *ctl)
+{
+  double *V = (double *)xcalloc((size_t)n_tmp * n, sizeof(double));
+  double *H = (double *)xcalloc((size_t)n_tmp * (n_tmp - 1), sizeof(double)); /* H(i,j) = H[i*(n_tmp-1)+j] */
+  double *gamma = (double *)xcalloc(n_tmp, sizeof(double));
+  double *ci = (double *)xcalloc(n_tmp, sizeof(double));
+  double *si = (double *)xcalloc(n_tmp, sizeof(double));
+  double *h = (double *)xcalloc(n_tmp, sizeof(double));
+  double *v = V;                             /* tmp_vectors(0) */
+  double *p = V + (size_t)(n_tmp - 1) * n;   /* tmp_vectors(n_tmp-1) */
+  const int nb = ctl->nb;
+  const int ldh = n_tmp - 1;
+  int accumulated = 0, state = 0, dim = 0;
+  int re_orth = 0;
+  do {
+    memset(h, 0, sizeof(double) * n_tmp);
+    A(Actx, x, p);
+    for (int i = 0; i < n; ++i) p[i] = -1.0 * p[i] + 1.0 * b[i]; /* p.sadd(-1, 1, b) */
+    P(Pctx, p, v);
+    double rho = sqrt(bdot(n, nb, v, v));
+    state = control_check(ctl, accumulated, rho);
+    if (state != 0) break;
+    gamma[0] = rho;
+    vscale(n, 1.0 / rho, v);
+    dim = 0;
+    for (int inner = 0; inner < n_tmp - 2 && state == 0; ++inner) {
+      ++accumulated;
+      double *vv = V + (size_t)(inner + 1) * n;
+      A(Actx, V + (size_t)inner * n, p);
+      P(Pctx, p, vv);
+      dim = inner + 1;
+      /* modified_gram_schmidt */
+      double norm_vv_start = 0.0;
+      const int consider = (!re_orth) && (inner % 5 == 4);
+      if (consider) norm_vv_start = sqrt(bdot(n, nb, vv, vv));
+      h[0] = bdot(n, nb, vv, V);
+      for (int i = 1; i < dim; ++i) {
+        vaxpy(n, -h[i - 1], V + (size_t)(i - 1) * n, vv);
+        h[i] = bdot(n, nb, vv, V + (size_t)i * n);
+      }
+      vaxpy(n, -h[dim - 1], V + (size_t)(dim - 1) * n, vv);
+      double s = sqrt(bdot(n, nb, vv, vv));
+      int done = 0;
+      if (consider) {
+        if (s > 10.0 * norm_vv_start * sqrt(2.220446049250313e-16)) done = 1;
+        else re_orth = 1;
+      }
+      if (!done && re_orth) {
+        double htmp = bdot(n, nb, vv, V);
+        h[0] += htmp;
+        for (int i = 1; i < dim; ++i) {
+          vaxpy(n, -htmp, V + (size_t)(i - 1) * n, vv);
+          htmp = bdot(n, nb, vv, V + (size_t)i * n);
+          h[i] += htmp;
+        }
+        vaxpy(n, -htmp, V + (size_t)(dim - 1) * n, vv);
+        s = sqrt(bdot(n, nb, vv, vv));
+      }
+      h[inner + 1] = s;
+      if (s != 0.0) vscale(n, 1.0 / s, vv);
+      givens_rotation(h, gamma, ci, si, inner);
+      for (int i = 0; i < dim; ++i) H[(size_t)i * ldh + inner] = h[i];
+      rho = fabs(gamma[dim]);
+      state = control_check(ctl, accumulated, rho);
+    }
+    /* H1.backward(h, gamma): upper-triangular solve with the dim x dim leading block */
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int j = i + 1; j < dim; ++j) s -= H[(size_t)i * ldh + j] * h[j];
+      h[i] = s / H[(size_t)i * ldh + i];
+    }
+    for (int i = 0; i < dim; ++i) vaxpy(n, h[i], V + (size_t)i * n, x);
+  } while (state == 0);
+  free(V); free(H); free(gamma); free(ci); free(si); free(h);
+  return state == 1 ? 0 : -1;
+}
+
+/* SolverCG::solve (deal.II 9.3/9.4 formulation: g = Ax - b, d = -P g) */
+static int cg_solve(int n, op_fn A, void *Actx, op_fn P, void *Pctx, double *x, const double *b, control_t *ctl)
+{
+  double *g = (double *)xcalloc(n, sizeof(double));
+  double *d = (double *)xcalloc(n, sizeof(double));
+  double *h = (double *)xcalloc(n, sizeof(double));
+  int it = 0, state;
+  int all_zero = 1;
+  for (int i = 0; i < n; ++i) if (x[i] != 0.0) { all_zero = 0; break; }
+  if (!all_zero) {
+    A(Actx, x, g);
+    vaxpy(n, -1.0, b, g);
+  } else
+    for (int i = 0; i < n; ++i) g[i] = -1.0 * b[i];
+  double res = sqrt(vdot(n, g, g));
+  state = control_check(ctl, 0, res);
+  if (state == 0) {
+    P(Pctx, g, h);
+    for (int i = 0; i < n; ++i) d[i] = -1.0 * h[i];
+    double gh = vdot(n, g, h);
+    while (state == 0) {
+      ++it;
+      A(Actx, d, h);
+      double alpha = vdot(n, d, h);
+      alpha = gh / alpha;
+      vaxpy(n, alpha, d, x);
+      vaxpy(n, alpha, h, g);
+      res = sqrt(fabs(vdot(n, g, g)));
+      state = control_check(ctl, it, res);
+      if (state != 0) break;
+      P(Pctx, g, h);
+      double beta = gh;
+      gh = vdot(n, g, h);
+      beta = gh / beta;
+      for (int i = 0; i < n; ++i) d[i] = beta * d[i] - 1.0 * h[i]; /* d.sadd(beta, -1, h) */
+    }
+  }
+  free(g); free(d); free(h);
+  return state == 1 ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* preconditioners (include/Preconditioners.hpp)                                              */
+/* ------------------------------------------------------------------------------------------ */
+static void op_csr(void *A, const double *x, double *y) { csr_vmult((const csr_t *)A, x, y); }
+
+static void op_system(void *vc, const double *x, double *y)
+{ /* BlockSparseMatrix::vmult with the blocks of system_matrix */
+  nso_ctx *c = (nso_ctx *)vc;
+  const int nu = c->nu, np = c->np;
+  double *t = (double *)xcalloc(nu, sizeof(double));
+  csr_vmult(&c->F, x, y);
+  csr_vmult(&c->Bt, x + nu, t);
+  vaxpy(nu, 1.0, t, y);
+  csr_vmult(&c->B, x, y + nu);
+  (void)np;
+  free(t);
+  c->n_vmult++;
+}
+
+static void inner_gmres(nso_ctx *c, const csr_t *A, ilu_t *ilu, double *x, const double *b, double tol, int is_F)
+{
+  control_t ctl;
+  memset(&ctl, 0, sizeof(ctl));
+  ctl.maxit = c->inner_maxit; ctl.tol = tol;
+  gmres_solve(A->n_rows, op_csr, (void *)A, ilu_apply, ilu, x, b, c->gmres_tmp, &ctl);
+  if (is_F) { c->n_inner_F += ctl.last_step; c->n_F_solves++; }
+  else { c->n_inner_S += ctl.last_step; c->n_S_solves++; }
+}
+static void inner_cg(nso_ctx *c, const csr_t *A, ilu_t *ilu, double *x, const double *b, double tol)
+{
+  control_t ctl;
+  memset(&ctl, 0, sizeof(ctl));
+  ctl.maxit = c->inner_maxit; ctl.tol = tol;
+  cg_solve(A->n_rows, op_csr, (void *)A, ilu_apply, ilu, x, b, &ctl);
+  c->n_inner_S += ctl.last_step; c->n_S_solves++;
+}
+
+/* PreconditionaSIMPLE::vmult, Preconditioners.hpp:254-311.  NOTE dst.block(0) is used as the  */
+/* initial guess of the F solve exactly as passed in (:273).                                  */
+static void asimple_vmult(void *vc, const double *src, double *dst)
+{
+  nso_ctx *c = (nso_ctx *)vc;
+  const int nu = c->nu, np = c->np;
+  const double *su = src, *sp = src + nu;
+  double *du = dst, *dp = dst + nu;
+  double *tmp_u = (double *)xcalloc(nu, sizeof(double));
+  double *tmp_p = (double *)xcalloc(np, sizeof(double));
+  inner_gmres(c, &c->F, &c->iluF, du, su, c->inner_rtol * sqrt(vdot(nu, su, su)), 1); /* :271-273 */
+  csr_vmult(&c->B, du, dp);                                                          /* :280 */
+  for (int i = 0; i < np; ++i) dp[i] = -1.0 * dp[i] + sp[i];                         /* :281 sadd(-1, src_p) */
+  vcopy(np, dp, tmp_p);                                                              /* :282 */
+  inner_gmres(c, &c->S, &c->iluS, dp, tmp_p, c->inner_rtol * sqrt(vdot(np, tmp_p, tmp_p)), 0); /* :287-289 */
+  for (int i = 0; i < nu; ++i) du[i] *= c->D[i];                                     /* :294 */
+  for (int i = 0; i < np; ++i) dp[i] /= c->alpha_asimple;                            /* :298 */
+  csr_vmult(&c->Bt, dp, tmp_u);                                                      /* :304 */
+  for (int i = 0; i < nu; ++i) du[i] -= tmp_u[i];                                    /* :305 */
+  for (int i = 0; i < nu; ++i) du[i] *= c->Dinv[i];                                  /* :309 */
+  free(tmp_u); free(tmp_p);
+}
+
+/* PreconditionSIMPLE::vmult, Preconditioners.hpp:151-205 */
+static void simple_vmult(void *vc, const double *src, double *dst)
+{
+  nso_ctx *c = (nso_ctx *)vc;
+  const int nu = c->nu, np = c->np;
+  const double *su = src, *sp = src + nu;
+  double *du = dst, *dp = dst + nu;
+  double *sol1_u = (double *)xcalloc(nu, sizeof(double));
+  double *sol1_p = (double *)xcalloc(np, sizeof(double));
+  double *temp_1 = (double *)xcalloc(np, sizeof(double));
+  double *tmp = (double *)xcalloc(nu, sizeof(double));
+  vcopy(nu, su, sol1_u); vcopy(np, sp, sol1_p);                                        /* :168-169 */
+  inner_gmres(c, &c->F, &c->iluF, sol1_u, su, c->inner_rtol * sqrt(vdot(nu, su, su)), 1); /* :173 */
+  csr_vmult(&c->B, sol1_u, temp_1);                                                   /* :175 */
+  for (int i = 0; i < np; ++i) temp_1[i] -= sp[i];                                    /* :176 */
+  inner_cg(c, &c->S, &c->iluS, sol1_p, temp_1, c->inner_rtol * sqrt(vdot(np, temp_1, temp_1))); /* :179-182 */
+  for (int i = 0; i < np; ++i) dp[i] = sol1_p[i] * (1.0 / c->alpha_simple);           /* :194-195 */
+  vcopy(nu, sol1_u, du);                                                              /* :199 */
+  csr_vmult(&c->Bt, dp, tmp);                                                         /* :201 */
+  for (int i = 0; i < nu; ++i) tmp[i] *= c->Dinv[i];                                  /* :202 */
+  for (int i = 0; i < nu; ++i) du[i] -= tmp[i];                                       /* :203 */
+  free(sol1_u); free(sol1_p); free(temp_1); free(tmp);
+}
+
+/* PreconditionYosida::vmult, Preconditioners.hpp:364-408 */
+static void yosida_vmult(void *vc, const double *src, double *dst)
+{
+  nso_ctx *c = (nso_ctx *)vc;
+  const int nu = c->nu, np = c->np;
+  const double *su = src, *sp = src + nu;
+  double *du = dst, *dp = dst + nu;
+  double *yu = (double *)xcalloc(nu, sizeof(double));
+  double *yp = (double *)xcalloc(np, sizeof(double));
+  double *tmp = (double *)xcalloc(np, sizeof(double));
+  double *tmp2 = (double *)xcalloc(nu, sizeof(double));
+  double *res = (double *)xcalloc(nu, sizeof(double));
+  vcopy(nu, su, yu); vcopy(np, sp, yp);                                               /* :375-376 */
+  inner_gmres(c, &c->F, &c->iluF, yu, su, c->inner_rtol * sqrt(vdot(nu, su, su)), 1); /* :371-382 */
+  csr_vmult(&c->B, yu, tmp);                                                          /* :385 */
+  for (int i = 0; i < np; ++i) tmp[i] += -1.0 * sp[i];                                /* :386 tmp.add(-1, src_p) */
+  inner_cg(c, &c->S, &c->iluS, yp, tmp, c->inner_rtol * sqrt(vdot(np, tmp, tmp)));    /* :388-390 */
+  vcopy(np, yp, dp);                                                                  /* :394 */
+  csr_vmult(&c->Bt, dp, tmp2);                                                        /* :398 */
+  /* res.reinit(...) zero initial guess (:401); dst_u = yu (:402) */
+  inner_gmres(c, &c->F, &c->iluF, res, tmp2, c->inner_rtol * sqrt(vdot(nu, tmp2, tmp2)), 1); /* :403-405 */
+  for (int i = 0; i < nu; ++i) du[i] = -1.0 * yu[i] + res[i];                         /* :406 sadd(-1, res) */
+  free(yu); free(yp); free(tmp); free(tmp2); free(res);
+}
+
+/* PreconditionaYosida::vmult, Preconditioners.hpp:474-517 */
+static void ayosida_vmult(void *vc, const double *src, double *dst)
+{
+  nso_ctx *c = (nso_ctx *)vc;
+  const int nu = c->nu, np = c->np;
+  const double *su = src, *sp = src + nu;
+  double *du = dst, *dp = dst + nu;
+  double *tmp = (double *)xcalloc(nu, sizeof(double));
+  double *tmp2 = (double *)xcalloc(np, sizeof(double));
+  double *yu = (double *)xcalloc(nu, sizeof(double));
+  double *yp = (double *)xcalloc(np, sizeof(double));
+  double *t3 = (double *)xcalloc(nu, sizeof(double));
+  for (int i = 0; i < nu; ++i) tmp[i] = su[i] * c->Dinv[i];                           /* :491-492 */
+  vcopy(nu, tmp, yu);                                                                 /* :493 */
+  vcopy(np, sp, yp);                                                                  /* :487 */
+  csr_vmult(&c->B, tmp, tmp2);                                                        /* :496 */
+  for (int i = 0; i < np; ++i) yp[i] = -1.0 * yp[i] + tmp2[i];                        /* :497 yp.sadd(-1, tmp2) */
+  inner_cg(c, &c->S, &c->iluS, dp, yp, c->inner_rtol * sqrt(vdot(np, yp, yp)));       /* :500-502, x0 = dst_p */
+  vcopy(np, dp, yp);                                                                  /* :504 */
+  csr_vmult(&c->F, yu, t3); vcopy(nu, t3, yu);                                        /* :507 F->vmult(yu, yu) */
+  csr_vmult(&c->Bt, yp, tmp);                                                         /* :510 */
+  for (int i = 0; i < nu; ++i) yu[i] = -1.0 * yu[i] + tmp[i];                         /* :511 yu.sadd(-1, tmp) */
+  for (int i = 0; i < nu; ++i) yu[i] *= c->Dinv[i];                                   /* :514 */
+  vcopy(nu, yu, du);                                                                  /* :515 */
+  free(tmp); free(tmp2); free(yu); free(yp); free(t3);
+}
+
+static double diag_of(const csr_t *A, int i)
+{
+  const int p = find_pos(A->rowptr, A->colind, i, i);
+  return p >= 0 ? A->val[p] : 0.0;
+}
+
+/* Preconditioner*::initialize.  ptype: 0 Yosida, 1 SIMPLE, 2 aYosida, 3 aSIMPLE              */
+/* (switch in NavierStokes2D.cpp:547-619)                                                     */
+NSO_API int nso_precond_init(nso_ctx *c, int ptype)
+{
+  free_solve_views(c);
+  const int nu = c->nu, N = c->N;
+  extract_block(c, c->sys, 0, nu, 0, nu, &c->F);
+  extract_block(c, c->sys, 0, nu, nu, N, &c->Bt);
+  extract_block(c, c->sys, nu, N, 0, nu, &c->B);
+  c->D = (double *)xcalloc(nu, sizeof(double));
+  c->Dinv = (double *)xcalloc(nu, sizeof(double));
+  c->negDinv = (double *)xcalloc(nu, sizeof(double));
+  if (ptype == 0) { /* Yosida: D = diag(mass_matrix.block(0,0)) (:350-355) */
+    for (int i = 0; i < nu; ++i) {
+      const int p = find_pos(c->rowptr, c->colind, i, i);
+      const double m = c->mass[p];
+      c->D[i] = m; c->Dinv[i] = 1.0 / m; c->negDinv[i] = -1.0 / m;
+    }
+  } else if (ptype == 2) { /* aYosida: Dinv from diag(F) (:447-452), lumped |M| for S (:456-465) */
+    for (int i = 0; i < nu; ++i) {
+      const double t = diag_of(&c->F, i);
+      c->D[i] = t; c->Dinv[i] = 1.0 / t;
+      double s = 0.0;
+      for (int p = c->rowptr[i]; p < c->rowptr[i + 1]; ++p)
+        if (c->colind[p] < nu) s += fabs(c->mass[p]);
+      c->negDinv[i] = -1.0 / s;
+    }
+  } else { /* SIMPLE / aSIMPLE: D = diag(F) (:135-140, :239-245) */
+    for (int i = 0; i < nu; ++i) {
+      const double t = diag_of(&c->F, i);
+      c->D[i] = t; c->Dinv[i] = 1.0 / t; c->negDinv[i] = -1.0 / t;
+    }
+  }
+  csr_mmult_diag(&c->B, c->negDinv, &c->Bt, &c->S); /* B->mmult(neg_S, *B_T, neg_diag_D_inv) */
+  int *partS = NULL;
+  if (c->part) partS = c->part + nu;
+  ilu_factor(&c->F, c->part, &c->iluF);
+  ilu_factor(&c->S, partS, &c->iluS);
+  return 0;
+}
+
+/* Apply the preconditioner once (for parity tests of P.vmult alone) */
+NSO_API void nso_precond_vmult(nso_ctx *c, int ptype, const double *src, double *dst)
+{
+  switch (ptype) {
+    case 0: yosida_vmult(c, src, dst); break;
+    case 1: simple_vmult(c, src, dst); break;
+    case 2: ayosida_vmult(c, src, dst); break;
+    default: asimple_vmult(c, src, dst); break;
+  }
+}
+
+NSO_API void nso_system_vmult(nso_ctx *c, const double *x, double *y) { op_system(c, x, y); }
+NSO_API void nso_ilu_apply(nso_ctx *c, int which, const double *x, double *y)
+{
+  ilu_apply(which == 0 ? &c->iluF : &c->iluS, x, y);
+}
+NSO_API void nso_block_vmult(nso_ctx *c, int which, const double *x, double *y)
+{
+  const csr_t *A = which == 0 ? &c->F : which == 1 ? &c->Bt : which == 2 ? &c->B : &c->S;
+  csr_vmult(A, x, y);
+}
+
+/* NavierStokes::solve_time_step: previous_solution = solution; P.initialize; GMRES; solution = solution_owned */
+NSO_API int nso_solve_step(nso_ctx *c, int ptype, int *outer_its, double *last_res)
+{
+  memcpy(c->prev_sol, c->sol, sizeof(double) * c->N);
+  c->n_inner_F = c->n_inner_S = c->n_F_solves = c->n_S_solves = c->n_vmult = 0;
+  c->n_res_hist = 0;
+  nso_precond_init(c, ptype);
+  control_t ctl;
+  memset(&ctl, 0, sizeof(ctl));
+  ctl.maxit = c->outer_maxit; ctl.tol = c->outer_tol; ctl.hist = c; ctl.nb = c->nu;
+  op_fn P = ptype == 0 ? yosida_vmult : ptype == 1 ? simple_vmult : ptype == 2 ? ayosida_vmult : asimple_vmult;
+  const int rc = gmres_solve(c->N, op_system, c, P, c, c->sol_owned, c->rhs, c->gmres_tmp, &ctl);
+  if (outer_its) *outer_its = ctl.last_step;
+  if (last_res) *last_res = ctl.last_value;
+  memcpy(c->sol, c->sol_owned, sizeof(double) * c->N);
+  return rc;
+}
+
+NSO_API int nso_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
