@@ -1,0 +1,739 @@
+// kernels_linalg.cu -- bandwidth-bound sparse / dense vector kernels (sm_100a, FP64).
+//
+// Replaces what the reference gets from Trilinos through deal.II's wrappers:
+//   Epetra_CrsMatrix::Multiply (SparseMatrix::vmult; Preconditioners.hpp:280,304; the block
+//   vmult inside SolverGMRES, NavierStokes2D.cpp:609), Epetra vector ops, Ifpack_ILU
+//   (PreconditionILU, Preconditioners.hpp:250-251) and EpetraExt MatrixMatrix::Multiply
+//   (SparseMatrix::mmult, Preconditioners.hpp:248,358).
+// Layout: the velocity block is stored once as the scalar node graph F_s and applied to the
+// `dim` interleaved components of each P2 node; B / Bt keep `dim` values per (vertex,node) pair.
+#include <algorithm>
+#include <cstring>
+
+#include "nsb_internal.hpp"
+
+namespace nsb {
+
+constexpr int kSM = 148;
+
+// --------------------------------------------------------------------------------------------
+// SpMV
+// --------------------------------------------------------------------------------------------
+template <int DIM, int LPR>
+__global__ void __launch_bounds__(256) spmv_F_kernel(int n_rows, const int *__restrict__ rowptr,
+                                                     const int *__restrict__ colind, const double *__restrict__ val,
+                                                     const double *__restrict__ xu, int n_nodes_owned, int goff_u,
+                                                     const int *__restrict__ bt_rowptr,
+                                                     const int *__restrict__ bt_colind,
+                                                     const double *__restrict__ bt_val, const double *__restrict__ xp,
+                                                     int n_p_owned, int goff_p, double *__restrict__ yu)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sl = tid % LPR;
+  if (row >= n_rows) return;
+  double acc[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+  const int e = rowptr[row + 1];
+  for (int k = rowptr[row] + sl; k < e; k += LPR) {
+    const int c = colind[k];
+    const double v = val[k];
+    const double *xb = xu + int64_t(DIM) * c + (c >= n_nodes_owned ? goff_u : 0);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] += v * xb[d];
+  }
+  if (xp) {
+    const int e2 = bt_rowptr[row + 1];
+    for (int k = bt_rowptr[row] + sl; k < e2; k += LPR) {
+      const int c = bt_colind[k];
+      const double x = xp[c + (c >= n_p_owned ? goff_p : 0)];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) acc[d] += bt_val[int64_t(k) * DIM + d] * x;
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, LPR);
+  if (sl == 0) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) yu[int64_t(DIM) * row + d] = acc[d];
+  }
+}
+
+template <int DIM, int LPR>
+__global__ void __launch_bounds__(256) spmv_B_kernel(int n_rows, const int *__restrict__ rowptr,
+                                                     const int *__restrict__ colind, const double *__restrict__ val,
+                                                     const double *__restrict__ xu, int n_nodes_owned, int goff_u,
+                                                     double *__restrict__ yp)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sl = tid % LPR;
+  if (row >= n_rows) return;
+  double acc = 0.0;
+  const int e = rowptr[row + 1];
+  for (int k = rowptr[row] + sl; k < e; k += LPR) {
+    const int c = colind[k];
+    const double *xb = xu + int64_t(DIM) * c + (c >= n_nodes_owned ? goff_u : 0);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc += val[int64_t(k) * DIM + d] * xb[d];
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+  if (sl == 0) yp[row] = acc;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) spmv_csr_kernel(int n_rows, const int *__restrict__ rowptr,
+                                                       const int *__restrict__ colind, const double *__restrict__ val,
+                                                       const double *__restrict__ x, int n_owned, int goff,
+                                                       double *__restrict__ y)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sl = tid % LPR;
+  if (row >= n_rows) return;
+  double acc = 0.0;
+  const int e = rowptr[row + 1];
+  for (int k = rowptr[row] + sl; k < e; k += LPR) {
+    const int c = colind[k];
+    acc += val[k] * x[c + (c >= n_owned ? goff : 0)];
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+  if (sl == 0) y[row] = acc;
+}
+
+static inline unsigned grid_for(int64_t threads, int block) { return unsigned((threads + block - 1) / block); }
+
+void spmv_F(Handle &H, const double *x_u, int goff_u, const double *x_p, int goff_p, double *y_u)
+{
+  const int n = H.n_nodes_owned;
+  if (n == 0) return;
+  constexpr int LPR = 8;
+  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
+  if (H.dim == 2)
+    spmv_F_kernel<2, LPR><<<grid, 256, 0, H.stream>>>(n, H.Fs.rowptr.p, H.Fs.colind.p, H.Fs.val.p, x_u,
+                                                      H.n_nodes_owned, goff_u, H.Bt.rowptr.p, H.Bt.colind.p,
+                                                      H.Bt.val.p, x_p, H.n_p_owned, goff_p, y_u);
+  else
+    spmv_F_kernel<3, LPR><<<grid, 256, 0, H.stream>>>(n, H.Fs.rowptr.p, H.Fs.colind.p, H.Fs.val.p, x_u,
+                                                      H.n_nodes_owned, goff_u, H.Bt.rowptr.p, H.Bt.colind.p,
+                                                      H.Bt.val.p, x_p, H.n_p_owned, goff_p, y_u);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+template <int DIM, int LPR>
+__global__ void __launch_bounds__(256) spmv_Bt_kernel(int n_rows, const int *__restrict__ bt_rowptr,
+                                                      const int *__restrict__ bt_colind,
+                                                      const double *__restrict__ bt_val, const double *__restrict__ xp,
+                                                      int n_p_owned, int goff_p, double *__restrict__ yu)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LPR, sl = tid % LPR;
+  if (row >= n_rows) return;
+  double acc[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+  const int e2 = bt_rowptr[row + 1];
+  for (int k = bt_rowptr[row] + sl; k < e2; k += LPR) {
+    const int c = bt_colind[k];
+    const double x = xp[c + (c >= n_p_owned ? goff_p : 0)];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] += bt_val[int64_t(k) * DIM + d] * x;
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, LPR);
+  if (sl == 0) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) yu[int64_t(DIM) * row + d] = acc[d];
+  }
+}
+
+void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u)
+{
+  const int n = H.n_nodes_owned;
+  if (n == 0) return;
+  constexpr int LPR = 4;
+  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
+  if (H.dim == 2)
+    spmv_Bt_kernel<2, LPR><<<grid, 256, 0, H.stream>>>(n, H.Bt.rowptr.p, H.Bt.colind.p, H.Bt.val.p, x_p, H.n_p_owned,
+                                                       goff_p, y_u);
+  else
+    spmv_Bt_kernel<3, LPR><<<grid, 256, 0, H.stream>>>(n, H.Bt.rowptr.p, H.Bt.colind.p, H.Bt.val.p, x_p, H.n_p_owned,
+                                                       goff_p, y_u);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p)
+{
+  const int n = H.n_p_owned;
+  if (n == 0) return;
+  constexpr int LPR = 16;
+  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
+  if (H.dim == 2)
+    spmv_B_kernel<2, LPR><<<grid, 256, 0, H.stream>>>(n, H.B.rowptr.p, H.B.colind.p, H.B.val.p, x_u, H.n_nodes_owned,
+                                                      goff_u, y_p);
+  else
+    spmv_B_kernel<3, LPR><<<grid, 256, 0, H.stream>>>(n, H.B.rowptr.p, H.B.colind.p, H.B.val.p, x_u, H.n_nodes_owned,
+                                                      goff_u, y_p);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+void spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p)
+{
+  const int n = H.n_p_owned;
+  if (n == 0) return;
+  constexpr int LPR = 16;
+  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
+  spmv_csr_kernel<LPR><<<grid, 256, 0, H.stream>>>(n, H.S.rowptr.p, H.S.colind.p, H.S.val.p, x_p, H.n_p_owned,
+                                                   goff_p, y_p);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+// --------------------------------------------------------------------------------------------
+// dense vector kernels
+// --------------------------------------------------------------------------------------------
+#define GRID_STRIDE(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
+
+static inline unsigned vgrid(int n) { return unsigned(std::max(1, std::min((n + 255) / 256, kSM * 8))); }
+
+__global__ void k_copy(int n, const double *__restrict__ x, double *__restrict__ y) { GRID_STRIDE(i, n) y[i] = x[i]; }
+__global__ void k_zero(int n, double *__restrict__ x) { GRID_STRIDE(i, n) x[i] = 0.0; }
+__global__ void k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)
+{ GRID_STRIDE(i, n) y[i] += a * x[i]; }
+__global__ void k_axpy_dev(int n, const double *__restrict__ a, double sign, const double *__restrict__ x,
+                           double *__restrict__ y)
+{
+  const double aa = sign * (*a);
+  GRID_STRIDE(i, n) y[i] += aa * x[i];
+}
+__global__ void k_sadd(int n, double s, double a, const double *__restrict__ x, double *__restrict__ y)
+{ GRID_STRIDE(i, n) y[i] = s * y[i] + a * x[i]; }
+__global__ void k_scale(int n, double a, double *__restrict__ x) { GRID_STRIDE(i, n) x[i] *= a; }
+__global__ void k_scale_inv_dev(int n, const double *__restrict__ s, double *__restrict__ x)
+{
+  const double a = 1.0 / (*s);
+  GRID_STRIDE(i, n) x[i] *= a;
+}
+__global__ void k_pointwise(int n, const double *__restrict__ d, double *__restrict__ x) { GRID_STRIDE(i, n) x[i] *= d[i]; }
+__global__ void k_pointwise_out(int n, const double *__restrict__ d, const double *__restrict__ x,
+                                double *__restrict__ y)
+{ GRID_STRIDE(i, n) y[i] = d[i] * x[i]; }
+
+void vec_copy(Handle &H, int n, const double *x, double *y)
+{
+  if (n <= 0 || x == y) return;
+  k_copy<<<vgrid(n), 256, 0, H.stream>>>(n, x, y); H.launches++;
+}
+void vec_zero(Handle &H, int n, double *x)
+{
+  if (n <= 0) return;
+  k_zero<<<vgrid(n), 256, 0, H.stream>>>(n, x); H.launches++;
+}
+void vec_axpy(Handle &H, int n, double a, const double *x, double *y)
+{
+  if (n <= 0) return;
+  k_axpy<<<vgrid(n), 256, 0, H.stream>>>(n, a, x, y); H.launches++;
+}
+void vec_axpy_dev(Handle &H, int n, const double *a_dev, double sign, const double *x, double *y)
+{
+  if (n <= 0) return;
+  k_axpy_dev<<<vgrid(n), 256, 0, H.stream>>>(n, a_dev, sign, x, y); H.launches++;
+}
+void vec_sadd(Handle &H, int n, double s, double a, const double *x, double *y)
+{
+  if (n <= 0) return;
+  k_sadd<<<vgrid(n), 256, 0, H.stream>>>(n, s, a, x, y); H.launches++;
+}
+void vec_scale(Handle &H, int n, double a, double *x)
+{
+  if (n <= 0) return;
+  k_scale<<<vgrid(n), 256, 0, H.stream>>>(n, a, x); H.launches++;
+}
+void vec_scale_inv_dev(Handle &H, int n, const double *s_dev, double *x)
+{
+  if (n <= 0) return;
+  k_scale_inv_dev<<<vgrid(n), 256, 0, H.stream>>>(n, s_dev, x); H.launches++;
+}
+void vec_pointwise(Handle &H, int n, const double *d, double *x)
+{
+  if (n <= 0) return;
+  k_pointwise<<<vgrid(n), 256, 0, H.stream>>>(n, d, x); H.launches++;
+}
+void vec_pointwise_out(Handle &H, int n, const double *d, const double *x, double *y)
+{
+  if (n <= 0) return;
+  k_pointwise_out<<<vgrid(n), 256, 0, H.stream>>>(n, d, x, y); H.launches++;
+}
+
+// Deterministic two-stage reduction: fixed grid, fixed per-block order, the last block to finish
+// (ticket) adds the block partials in index order.  scratch layout: [0..1023] partials, then ticket.
+constexpr int kRedBlocks = 592; // 148 * 4
+__device__ __forceinline__ double block_sum(double v)
+{
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x < 32) {
+    s = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  return s; // valid in thread 0
+}
+
+__device__ __forceinline__ void finish_reduce(double part, double *partials, unsigned *ticket, double *out)
+{
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = part;
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    double v = 0.0;
+    // fixed order: thread t sums partials t, t+256, ...; then block tree
+    for (int b = threadIdx.x; b < int(gridDim.x); b += blockDim.x) v += __ldcg(partials + b);
+    const double s = block_sum(v);
+    if (threadIdx.x == 0) { *out = s; *ticket = 0u; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ x, const double *__restrict__ y,
+                                             double *partials, unsigned *ticket, double *out)
+{
+  double v = 0.0;
+  GRID_STRIDE(i, n) v += x[i] * y[i];
+  const double s = block_sum(v);
+  finish_reduce(s, partials, ticket, out);
+}
+
+__global__ void __launch_bounds__(256) k_add_and_dot(int n, double *vv, const double *__restrict__ a,
+                                                     double sign, const double *__restrict__ vp,
+                                                     const double *vn, double *partials,
+                                                     unsigned *ticket, double *out)
+{
+  const double aa = sign * (*a);
+  double v = 0.0;
+  GRID_STRIDE(i, n) {
+    const double t = vv[i] + aa * vp[i];
+    const double o = (vn == vv) ? t : vn[i];
+    vv[i] = t;
+    v += t * o;
+  }
+  const double s = block_sum(v);
+  finish_reduce(s, partials, ticket, out);
+}
+
+static inline unsigned rgrid(int n) { return unsigned(std::max(1, std::min((n + 255) / 256, kRedBlocks))); }
+
+void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev)
+{
+  double *partials = H.d_scratch.p + 64;
+  unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024);
+  k_dot<<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), x, y, partials, ticket, out_dev);
+  H.launches++;
+}
+
+void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
+                         const double *v_next, double *out_dev)
+{
+  double *partials = H.d_scratch.p + 64;
+  unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024);
+  k_add_and_dot<<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), vv, a_dev, sign, v_prev, v_next, partials, ticket,
+                                                out_dev);
+  H.launches++;
+}
+
+// --------------------------------------------------------------------------------------------
+// ILU(0): Ifpack_ILU::Compute / Solve on the device, level scheduled
+// --------------------------------------------------------------------------------------------
+static void level_schedule(int n, const std::vector<int> &rowptr, const std::vector<int> &colind, bool forward,
+                           std::vector<int> &lvl_ptr, std::vector<int> &lvl_rows)
+{
+  std::vector<int> level(n, 0);
+  int maxl = 0;
+  if (forward) {
+    for (int i = 0; i < n; ++i) {
+      int l = 0;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colind[k];
+        if (j < i) l = std::max(l, level[j] + 1);
+      }
+      level[i] = l;
+      maxl = std::max(maxl, l);
+    }
+  } else {
+    for (int i = n - 1; i >= 0; --i) {
+      int l = 0;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colind[k];
+        if (j > i) l = std::max(l, level[j] + 1);
+      }
+      level[i] = l;
+      maxl = std::max(maxl, l);
+    }
+  }
+  const int nl = n ? maxl + 1 : 0;
+  lvl_ptr.assign(nl + 1, 0);
+  for (int i = 0; i < n; ++i) lvl_ptr[level[i] + 1]++;
+  for (int l = 0; l < nl; ++l) lvl_ptr[l + 1] += lvl_ptr[l];
+  lvl_rows.resize(n);
+  std::vector<int> pos(lvl_ptr.begin(), lvl_ptr.end() - (nl ? 1 : 0));
+  if (forward)
+    for (int i = 0; i < n; ++i) lvl_rows[pos[level[i]]++] = i;
+  else
+    for (int i = n - 1; i >= 0; --i) lvl_rows[pos[level[i]]++] = i;
+}
+
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs)
+{
+  const int n = A.n_rows;
+  ilu.n = n;
+  ilu.bs_rhs = bs_rhs;
+  std::vector<int> rowptr(n + 1, 0), colind, src, diagpos(n, 0);
+  colind.reserve(A.colind.size());
+  src.reserve(A.colind.size());
+  for (int i = 0; i < n; ++i) {
+    bool have_diag = false;
+    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+      const int j = A.colind[k];
+      if (j >= n_owned_cols) continue; // Ifpack_LocalFilter: off-process columns are dropped
+      if (j == i) have_diag = true;
+      colind.push_back(j);
+      src.push_back(k);
+    }
+    if (!have_diag) throw StateError("ILU: structurally missing diagonal");
+    rowptr[i + 1] = int(colind.size());
+    int dp = rowptr[i];
+    while (colind[dp] != i) ++dp;
+    diagpos[i] = dp;
+  }
+  ilu.nnz = int64_t(colind.size());
+  ilu.rowptr.upload(rowptr);
+  ilu.colind.upload(colind);
+  ilu.src.upload(src);
+  ilu.diagpos.upload(diagpos);
+  ilu.val.alloc(colind.size());
+  ilu.dinv.alloc(n);
+  std::vector<int> rows;
+  level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);
+  ilu.lvl_rows_f.upload(rows);
+  level_schedule(n, rowptr, colind, false, ilu.lvl_ptr_b, rows);
+  ilu.lvl_rows_b.upload(rows);
+  (void)H;
+}
+
+__global__ void k_gather(int64_t n, const int *__restrict__ src, const double *__restrict__ a, double *__restrict__ out)
+{
+  for (int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; k < n; k += int64_t(gridDim.x) * blockDim.x)
+    out[k] = a[src[k]];
+}
+
+// One warp per row of the current level.  Row i is updated in place in global memory: entries of
+// rows of earlier levels are final (L scaled by dinv_j, U scaled by dinv_i as Ifpack stores them).
+__global__ void __launch_bounds__(128) k_ilu_factor_level(int n_rows_lvl, const int *__restrict__ rows,
+                                                          const int *__restrict__ rowptr,
+                                                          const int *__restrict__ colind,
+                                                          const int *__restrict__ diagpos, double *__restrict__ val,
+                                                          double *__restrict__ dinv)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_rows_lvl) return;
+  const int i = rows[w];
+  const int rs = rowptr[i], re = rowptr[i + 1], dp = diagpos[i];
+  for (int jj = rs; jj < dp; ++jj) {
+    const int j = colind[jj];
+    const double multiplier = val[jj];
+    const int js = diagpos[j] + 1, je = rowptr[j + 1];
+    for (int k = js + lane; k < je; k += 32) {
+      const int col = colind[k];
+      // binary search for col in (jj, re) of row i
+      int lo = jj + 1, hi = re - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, c = colind[mid];
+        if (c == col) { val[mid] -= multiplier * val[k]; break; }
+        if (c < col) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) val[jj] = multiplier * dinv[j];
+    __syncwarp();
+  }
+  double d = val[dp];
+  const double MinDiag = 2.2250738585072014e-308, MaxDiag = 1.0 / MinDiag;
+  if (fabs(d) > MaxDiag) d = (d < 0) ? -MinDiag : MinDiag; else d = 1.0 / d;
+  __syncwarp();
+  for (int k = dp + 1 + lane; k < re; k += 32) val[k] *= d;
+  if (lane == 0) dinv[i] = d;
+}
+
+void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val)
+{
+  if (ilu.n == 0) return;
+  cudaStream_t s = H.stream;
+  k_gather<<<unsigned(std::min<int64_t>((ilu.nnz + 255) / 256, kSM * 16)), 256, 0, s>>>(ilu.nnz, ilu.src.p, A_val,
+                                                                                       ilu.val.p);
+  H.launches++;
+  const int nl = int(ilu.lvl_ptr_f.size()) - 1;
+  for (int l = 0; l < nl; ++l) {
+    const int cnt = ilu.lvl_ptr_f[l + 1] - ilu.lvl_ptr_f[l];
+    k_ilu_factor_level<<<(cnt * 32 + 127) / 128, 128, 0, s>>>(cnt, ilu.lvl_rows_f.p + ilu.lvl_ptr_f[l], ilu.rowptr.p,
+                                                              ilu.colind.p, ilu.diagpos.p, ilu.val.p, ilu.dinv.p);
+    H.launches++;
+  }
+  NSB_CUDA(cudaGetLastError());
+}
+
+// Triangular solves, BS right-hand sides interleaved per row (BS = dim for F_s, 1 for S).
+template <int BS, int LPR>
+__global__ void __launch_bounds__(128) k_trsv_fwd_level(int n_rows_lvl, const int *__restrict__ rows,
+                                                        const int *__restrict__ rowptr,
+                                                        const int *__restrict__ colind,
+                                                        const int *__restrict__ diagpos,
+                                                        const double *__restrict__ val, double *__restrict__ y)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = tid / LPR, sl = tid % LPR;
+  if (w >= n_rows_lvl) return;
+  const int i = rows[w];
+  double acc[BS];
+#pragma unroll
+  for (int d = 0; d < BS; ++d) acc[d] = 0.0;
+  const int e = diagpos[i];
+  for (int k = rowptr[i] + sl; k < e; k += LPR) {
+    const double v = val[k];
+    const double *yb = y + int64_t(BS) * colind[k];
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += v * yb[d];
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, LPR);
+  if (sl == 0) {
+#pragma unroll
+    for (int d = 0; d < BS; ++d) y[int64_t(BS) * i + d] -= acc[d];
+  }
+}
+
+template <int BS, int LPR>
+__global__ void __launch_bounds__(128) k_trsv_bwd_level(int n_rows_lvl, const int *__restrict__ rows,
+                                                        const int *__restrict__ rowptr,
+                                                        const int *__restrict__ colind,
+                                                        const int *__restrict__ diagpos,
+                                                        const double *__restrict__ val,
+                                                        const double *__restrict__ dinv, double *__restrict__ y)
+{
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = tid / LPR, sl = tid % LPR;
+  if (w >= n_rows_lvl) return;
+  const int i = rows[w];
+  double acc[BS];
+#pragma unroll
+  for (int d = 0; d < BS; ++d) acc[d] = 0.0;
+  const int e = rowptr[i + 1];
+  for (int k = diagpos[i] + 1 + sl; k < e; k += LPR) {
+    const double v = val[k];
+    const double *yb = y + int64_t(BS) * colind[k];
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += v * yb[d];
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, LPR);
+  if (sl == 0) {
+    const double di = dinv[i];
+#pragma unroll
+    for (int d = 0; d < BS; ++d) y[int64_t(BS) * i + d] = y[int64_t(BS) * i + d] * di - acc[d];
+  }
+}
+
+template <int BS>
+static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
+{
+  constexpr int LPR = 8;
+  const int nf = int(ilu.lvl_ptr_f.size()) - 1;
+  for (int l = 1; l < nf; ++l) { // level 0 rows have an empty L part
+    const int cnt = ilu.lvl_ptr_f[l + 1] - ilu.lvl_ptr_f[l];
+    k_trsv_fwd_level<BS, LPR><<<(cnt * LPR + 127) / 128, 128, 0, s>>>(cnt, ilu.lvl_rows_f.p + ilu.lvl_ptr_f[l],
+                                                                     ilu.rowptr.p, ilu.colind.p, ilu.diagpos.p,
+                                                                     ilu.val.p, y);
+  }
+  const int nb = int(ilu.lvl_ptr_b.size()) - 1;
+  for (int l = 0; l < nb; ++l) {
+    const int cnt = ilu.lvl_ptr_b[l + 1] - ilu.lvl_ptr_b[l];
+    k_trsv_bwd_level<BS, LPR><<<(cnt * LPR + 127) / 128, 128, 0, s>>>(cnt, ilu.lvl_rows_b.p + ilu.lvl_ptr_b[l],
+                                                                     ilu.rowptr.p, ilu.colind.p, ilu.diagpos.p,
+                                                                     ilu.val.p, ilu.dinv.p, y);
+  }
+  H.launches += (nf > 0 ? nf - 1 : 0) + nb;
+}
+
+// y = U^{-1} D^{-1} L^{-1} x.  The per-level launches are captured once into a CUDA graph that
+// works in place on a fixed staging vector (graph nodes bake their pointers).
+void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
+{
+  if (ilu.n == 0) return;
+  const int nvals = ilu.n * ilu.bs_rhs;
+  cudaStream_t s = H.stream;
+  if (!ilu.graph_f) {
+    NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * size_t(nvals)));
+    cudaGraph_t g;
+    const int64_t before = H.launches;
+    NSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    if (ilu.bs_rhs == 1) trsv_levels<1>(H, ilu, ilu.graph_x, s);
+    else if (ilu.bs_rhs == 2) trsv_levels<2>(H, ilu, ilu.graph_x, s);
+    else trsv_levels<3>(H, ilu, ilu.graph_x, s);
+    NSB_CUDA(cudaStreamEndCapture(s, &g));
+    NSB_CUDA(cudaGraphInstantiate(&ilu.graph_f, g, 0));
+    NSB_CUDA(cudaGraphDestroy(g));
+    H.launches = before;
+  }
+  NSB_CUDA(cudaMemcpyAsync(ilu.graph_x, x, sizeof(double) * size_t(nvals), cudaMemcpyDeviceToDevice, s));
+  NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
+  NSB_CUDA(cudaMemcpyAsync(y, ilu.graph_x, sizeof(double) * size_t(nvals), cudaMemcpyDeviceToDevice, s));
+  H.launches += (int64_t(ilu.lvl_ptr_f.size()) - 2 > 0 ? int64_t(ilu.lvl_ptr_f.size()) - 2 : 0) +
+                (int64_t(ilu.lvl_ptr_b.size()) - 1);
+}
+
+// --------------------------------------------------------------------------------------------
+// S = B diag(V) Bt on the static symbolic pattern (numeric phase of SparseMatrix::mmult).
+// One warp per pressure row; lanes own the Bt entries of the current node, so every S entry is
+// accumulated in the reference's order (B row entries ascending, components innermost).
+// --------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_spgemm_schur(int n_rows, const int *__restrict__ b_rowptr,
+                                                      const int *__restrict__ b_colind,
+                                                      const double *__restrict__ b_val,
+                                                      const double *__restrict__ V, int n_nodes_owned, int goff_u,
+                                                      const int *__restrict__ bt_rowptr,
+                                                      const int *__restrict__ bt_colind,
+                                                      const double *__restrict__ bt_val,
+                                                      const int *__restrict__ s_rowptr,
+                                                      const int *__restrict__ s_colind, double *__restrict__ s_val)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const int ss = s_rowptr[w], se = s_rowptr[w + 1];
+  for (int k = ss + lane; k < se; k += 32) s_val[k] = 0.0;
+  __syncwarp();
+  for (int e = b_rowptr[w]; e < b_rowptr[w + 1]; ++e) {
+    const int node = b_colind[e];
+    if (node >= n_nodes_owned) continue; // ghost rows of Bt are handled by the halo variant
+    double m[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) m[d] = b_val[int64_t(e) * DIM + d] * V[int64_t(DIM) * node + d];
+    for (int f = bt_rowptr[node] + lane; f < bt_rowptr[node + 1]; f += 32) {
+      const int col = bt_colind[f];
+      int lo = ss, hi = se - 1, pos = -1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, c = s_colind[mid];
+        if (c == col) { pos = mid; break; }
+        if (c < col) lo = mid + 1; else hi = mid - 1;
+      }
+      double acc = s_val[pos];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) acc += m[d] * bt_val[int64_t(f) * DIM + d];
+      s_val[pos] = acc;
+    }
+    __syncwarp();
+  }
+  (void)goff_u;
+}
+
+void spgemm_schur(Handle &H)
+{
+  const int n = H.n_p_owned;
+  if (n == 0) return;
+  const unsigned grid = grid_for(int64_t(n) * 32, 128);
+  if (H.dim == 2)
+    k_spgemm_schur<2><<<grid, 128, 0, H.stream>>>(n, H.B.rowptr.p, H.B.colind.p, H.B.val.p, H.d_negDinv.p,
+                                                  H.n_nodes_owned, H.ghost_off_u(), H.Bt.rowptr.p, H.Bt.colind.p,
+                                                  H.Bt.val.p, H.S.rowptr.p, H.S.colind.p, H.S.val.p);
+  else
+    k_spgemm_schur<3><<<grid, 128, 0, H.stream>>>(n, H.B.rowptr.p, H.B.colind.p, H.B.val.p, H.d_negDinv.p,
+                                                  H.n_nodes_owned, H.ghost_off_u(), H.Bt.rowptr.p, H.Bt.colind.p,
+                                                  H.Bt.val.p, H.S.rowptr.p, H.S.colind.p, H.S.val.p);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+// D, 1/D, -1/D per velocity DoF (Preconditioners.hpp:135-140, 239-245, 350-355, 447-465)
+template <int DIM>
+__global__ void k_extract_diag(int n_nodes, int ptype, const int *__restrict__ diagpos, const double *__restrict__ F,
+                               const double *__restrict__ massdiag, const double *__restrict__ masslump,
+                               double *__restrict__ D, double *__restrict__ Dinv, double *__restrict__ negDinv)
+{
+  GRID_STRIDE(i, n_nodes) {
+    double d, nd;
+    if (ptype == NSB_PREC_YOSIDA) { d = massdiag[i]; nd = -1.0 / d; }
+    else if (ptype == NSB_PREC_AYOSIDA) { d = F[diagpos[i]]; nd = -1.0 / masslump[i]; }
+    else { d = F[diagpos[i]]; nd = -1.0 / d; }
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      D[int64_t(DIM) * i + c] = d;
+      Dinv[int64_t(DIM) * i + c] = 1.0 / d;
+      negDinv[int64_t(DIM) * i + c] = nd;
+    }
+  }
+}
+
+void extract_diag(Handle &H)
+{
+  const int n = H.n_nodes_owned;
+  if (n == 0) return;
+  if (H.dim == 2)
+    k_extract_diag<2><<<vgrid(n), 256, 0, H.stream>>>(n, H.prm.precond_type, H.d_diagF.p, H.Fs.val.p, H.d_massdiag.p,
+                                                      H.d_masslump.p, H.d_D.p, H.d_Dinv.p, H.d_negDinv.p);
+  else
+    k_extract_diag<3><<<vgrid(n), 256, 0, H.stream>>>(n, H.prm.precond_type, H.d_diagF.p, H.Fs.val.p, H.d_massdiag.p,
+                                                      H.d_masslump.p, H.d_D.p, H.d_Dinv.p, H.d_negDinv.p);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+// mass-matrix diagonal and |row| sums on the F_s pattern (computed once after the first assembly)
+__global__ void k_mass_rows(int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ diagpos,
+                            const double *__restrict__ M, double *__restrict__ massdiag, double *__restrict__ masslump)
+{
+  GRID_STRIDE(i, n_nodes) {
+    double s = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) s += fabs(M[k]);
+    masslump[i] = s;
+    massdiag[i] = M[diagpos[i]];
+  }
+}
+
+void mass_rows(Handle &H)
+{
+  const int n = H.n_nodes_owned;
+  if (n == 0) return;
+  k_mass_rows<<<vgrid(n), 256, 0, H.stream>>>(n, H.Fs.rowptr.p, H.d_diagF.p, H.d_M.p, H.d_massdiag.p, H.d_masslump.p);
+  NSB_CUDA(cudaGetLastError());
+  H.launches++;
+}
+
+static DevBuf<double> g_flush;
+void flush_l2(Handle &H)
+{
+  const size_t n = size_t(256) << 20 >> 3; // 256 MiB > 126 MB L2
+  if (g_flush.n != n) g_flush.alloc(n);
+  k_zero<<<kSM * 8, 256, 0, H.stream>>>(int(n), g_flush.p);
+}
+
+} // namespace nsb

@@ -1,0 +1,259 @@
+// nsb_internal.hpp -- device-side state of one engine handle and the kernel launch wrappers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nsb.h"
+#include "nsb_host.hpp"
+
+namespace nsb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NoConvergence : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NcclError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define NSB_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      throw nsb::CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                           std::to_string(__LINE__) + ")");                                        \
+  } while (0)
+
+constexpr int kMaxQ = 16;
+
+// reference-element tables, uploaded once (nsb_set_quadrature)
+struct FeTables {
+  int nq;
+  double w[kMaxQ];
+  double phi[10][kMaxQ];     // P2 values      [node][q]
+  double dphi[10][kMaxQ][3]; // P2 ref. grads  [node][q][d]
+  double psi[4][kMaxQ];      // P1 values      [vertex][q]
+};
+
+// Pre-contracted reference tensors for the step assembly ("assemble_step"):
+//   C_ij = |detJ| * sum_{a,k} T[i][j][a][k] * (J^{-1} U_a)[k]
+//   T[i][j][a][k] = sum_q w_q phi_i (dphi_j[k] phi_a  +  temam/2 * phi_j dphi_a[k])
+//   rhs_i[c] = |detJ|/dt * sum_a Mh[i][a] U_a[c],  Mh[i][a] = sum_q w_q phi_i phi_a
+struct StepTensor {
+  double T[10][10][10][3];
+  double Mh[10][10];
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count)
+  {
+    release();
+    n = count;
+    if (count) NSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T> &h)
+  {
+    if (n != h.size()) alloc(h.size());
+    if (n) NSB_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void zero(cudaStream_t s = 0)
+  {
+    if (n) NSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// CSR on the device; `bs` doubles per stored entry (1 for F_s, Mp, S; dim for B and Bt).
+struct DevCsr {
+  int n_rows = 0, n_cols = 0, bs = 1;
+  int64_t nnz = 0;
+  DevBuf<int> rowptr, colind;
+  DevBuf<double> val;
+  void upload_pattern(const Csr &h, int bs_)
+  {
+    n_rows = h.n_rows; n_cols = h.n_cols; bs = bs_; nnz = h.nnz();
+    rowptr.upload(h.rowptr);
+    colind.upload(h.colind);
+    val.alloc(size_t(nnz) * bs);
+    val.zero();
+  }
+};
+
+// ILU(0) factors in Ifpack's storage convention (strict lower part = a_ij * dinv_j, strict upper
+// part scaled by dinv_i, inverse diagonal separate), on the owned-columns pattern, plus the
+// level schedules of the two triangular solves.
+struct DevIlu {
+  int n = 0, bs_rhs = 1;
+  int64_t nnz = 0;
+  DevBuf<int> rowptr, colind, diagpos; // diagpos[i]: first entry with col > i  (end of L part)
+  DevBuf<int> src;                     // position of each entry in the source matrix
+  DevBuf<double> val, dinv;
+  // forward (L / factorisation) and backward (U) level schedules
+  std::vector<int> lvl_ptr_f, lvl_ptr_b;
+  DevBuf<int> lvl_rows_f, lvl_rows_b;
+  // chunked persistent schedule (sptrsv_kernel = 2)
+  DevBuf<int> chunk_ptr_f, chunk_ptr_b, chunk_lvl_ptr_f, chunk_lvl_ptr_b, chunk_rows_f, chunk_rows_b;
+  DevBuf<int> chunk_dep_ptr_f, chunk_dep_f, chunk_dep_ptr_b, chunk_dep_b;
+  DevBuf<int> chunk_flags, chunk_ticket;
+  int n_chunks = 0;
+  int max_chunk_rows = 0;
+  cudaGraphExec_t graph_f = nullptr, graph_b = nullptr; // per-level launches captured once
+  double *graph_x = nullptr;
+};
+
+struct Halo; // multi-rank exchange (halo.cu)
+
+struct Handle {
+  int dim = 0, n2 = 0, nv1 = 0, dpc = 0;
+  int device = 0, nranks = 1, rank = 0;
+  std::string err;
+  nsb_params prm{};
+  bool have_mesh = false, have_quad = false, finalized = false, assembled = false, prec_ready = false;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+
+  // ---- host copies of the static problem description
+  int64_t nc = 0, nc_pad = 0;
+  int n_nodes = 0, n_p = 0, n_nodes_owned = 0, n_p_owned = 0;
+  std::vector<double> h_vcoords;
+  std::vector<int> h_cell_nodes, h_cell_p;
+  Csr hFs, hB, hBt, hMp, hS;
+  FeTables h_tab{};
+  std::vector<int> h_dir_nodes; // constrained P2 nodes (owned)
+  std::vector<int> h_dir_rows;  // as given by the caller (dof = dim*node + c)
+  std::vector<int> h_dir_slot;  // caller row k -> slot in d_dir_vals (node-major, comp-minor)
+
+  // ---- layout of local vectors: [u owned | p owned | u ghost | p ghost]
+  int nu_owned() const { return dim * n_nodes_owned; }
+  int n_owned() const { return dim * n_nodes_owned + n_p_owned; }
+  int n_local() const { return dim * n_nodes + n_p; }
+  // offset added to dim*node when node >= n_nodes_owned
+  int ghost_off_u() const { return n_p_owned; }
+  // pressure p lives at p_base() + p (+ ghost_off_p() when p >= n_p_owned)
+  int p_base() const { return dim * n_nodes_owned; }
+  int ghost_off_p() const { return dim * (n_nodes - n_nodes_owned); }
+
+  // ---- device: mesh
+  DevBuf<double> d_vcoords;       // [nc_pad/32][(dim+1)*dim][32]  (cell-interleaved, coalesced)
+  DevBuf<int> d_cell_nodes;       // [nc_pad/32][n2][32]
+  DevBuf<int> d_cell_p;           // [nc_pad/32][nv1][32]
+  DevBuf<int> d_mapF;             // [nc_pad/32][n2*n2][32] position in F_s values, -1 = skip
+  DevBuf<FeTables> d_tab;
+  DevBuf<StepTensor> d_step_tensor;
+
+  // ---- device: matrices (compact layout, DESIGN.md "data layout")
+  DevCsr Fs;                      // system_matrix.block(0,0) = I_dim (x) F_s
+  DevBuf<double> d_K, d_M, d_A;   // K = M + A, mass/dt, stiffness on the F_s pattern
+  DevBuf<double> d_C;             // convection (parity harness only, lazily allocated)
+  DevCsr B, Bt, Mp, S;
+  DevBuf<int> d_diagF;            // position of the diagonal in each F_s row
+  DevBuf<double> d_massdiag, d_masslump;
+  DevBuf<double> d_D, d_Dinv, d_negDinv; // per velocity DoF (node-interleaved)
+  DevIlu iluF, iluS;
+  DevBuf<int> d_spgemm_ws;
+
+  // ---- device: boundary data
+  DevBuf<int> d_dir_nodes;
+  DevBuf<double> d_dir_vals;      // [n_dir_nodes][dim]
+  DevBuf<double> d_neumann;
+  bool have_neumann = false;
+
+  // ---- device: vectors (local layout)
+  DevBuf<double> d_sol, d_rhs;
+  DevBuf<double> d_scratch;       // reductions etc.
+  double *h_pinned = nullptr;     // pinned host scratch for scalars
+  std::vector<double> h_dir_vals;
+
+  Halo *halo = nullptr;
+
+  // ---- solver workspace (solver.cu)
+  struct SolverWs {
+    DevBuf<double> V_outer;   // n_tmp x n_local
+    DevBuf<double> V_inner;   // n_tmp x max(dim*n_nodes, n_p)
+    DevBuf<double> tu[4];     // velocity temporaries (layout U: [owned | ghost])
+    DevBuf<double> tp[6];     // pressure temporaries (layout P)
+    DevBuf<double> scal;      // device scalars: [0,64) outer GMRES, [64,128) inner, [128,192) CG, 200.. norms
+    DevBuf<double> prec_in, prec_out; // staging for the operator-level entry points
+  };
+  SolverWs *ws = nullptr;
+
+  // ---- statistics of the last solve
+  long n_inner_F = 0, n_inner_S = 0, n_F_solves = 0, n_S_solves = 0, n_vmult = 0;
+  int last_outer = 0;
+  double last_res = 0, t_assemble_ms = 0, t_prec_ms = 0, t_solve_ms = 0;
+
+  ~Handle();
+};
+
+// ---------------------------------------------------------------- kernels_assembly.cu
+void launch_assemble_first(Handle &H);
+void launch_assemble_step(Handle &H, double *F_target);
+void launch_apply_dirichlet(Handle &H, bool clear_bt);
+void build_step_tensor(const FeTables &tab, int dim, bool temam, StepTensor &out);
+
+// ---------------------------------------------------------------- kernels_linalg.cu
+// y_u = F_s x_u (+ Bt x_p when xp != nullptr).  x, y: local vectors (bases of the u blocks).
+// goff_u / goff_p: extra offset of ghost entries in the given vector (see Handle::ghost_off_*).
+void spmv_F(Handle &H, const double *x_u, int goff_u, const double *x_p, int goff_p, double *y_u);
+void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p);   // y_p = B x_u
+void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u);  // y_u = Bt x_p
+void spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p);
+void vec_copy(Handle &H, int n, const double *x, double *y);
+void vec_zero(Handle &H, int n, double *x);
+void vec_axpy(Handle &H, int n, double a, const double *x, double *y);             // y += a x
+void vec_axpy_dev(Handle &H, int n, const double *a_dev, double sign, const double *x, double *y);
+void vec_sadd(Handle &H, int n, double s, double a, const double *x, double *y);   // y = s y + a x
+void vec_scale(Handle &H, int n, double a, double *x);
+void vec_scale_inv_dev(Handle &H, int n, const double *s_dev, double *x);          // x /= *s_dev
+void vec_pointwise(Handle &H, int n, const double *d, double *x);                  // x *= d
+void vec_pointwise_out(Handle &H, int n, const double *d, const double *x, double *y); // y = d .* x
+// out_dev[0] = sum x_i y_i over n entries (this rank); deterministic two-stage reduction
+void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev);
+// vv += sign * (*a_dev) * v_prev ; out_dev = vv . v_next      (SolverGMRES add_and_dot)
+void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
+                         const double *v_next, double *out_dev);
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs);
+void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val);
+void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y); // y = U^-1 D^-1 L^-1 x
+void spgemm_schur(Handle &H); // S = B diag(negDinv) Bt on the static pattern
+void extract_diag(Handle &H);  // d_D / d_Dinv / d_negDinv per preconditioner type
+void mass_rows(Handle &H);     // d_massdiag / d_masslump from d_M
+void flush_l2(Handle &H);
+
+// ---------------------------------------------------------------- solver.cu
+void solver_alloc(Handle &H);
+void solver_free(Handle &H);
+void precond_init(Handle &H);
+void precond_vmult(Handle &H, const double *src, double *dst);
+void system_vmult(Handle &H, const double *x, double *y);
+int solve_outer(Handle &H);
+// all-reduce (sum) of `n` device doubles across ranks (no-op on one rank) and fetch to host
+void reduce_fetch(Handle &H, double *dev, int n, double *host_out);
+
+// ---------------------------------------------------------------- halo.cu
+void halo_create(Handle &H, const void *unique_id);
+void halo_destroy(Handle &H);
+void get_unique_id(void *out128);
+void halo_set_plan(Handle &H, int n_nb, const int *nb_rank, const int *send_node_ptr, const int *send_node_idx,
+                   const int *recv_node_cnt, const int *send_p_ptr, const int *send_p_idx, const int *recv_p_cnt);
+// fill the ghost entries of a velocity / pressure vector whose ghosts start at x + (owned) + goff
+void halo_exchange_u(Handle &H, double *x_u, int goff_u);
+void halo_exchange_p(Handle &H, double *x_p, int goff_p);
+void halo_allreduce(Handle &H, double *dev, int n);
+
+} // namespace nsb

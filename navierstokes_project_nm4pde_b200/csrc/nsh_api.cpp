@@ -1,0 +1,133 @@
+// nsh_api.cpp -- C ABI of the host prerequisites (mesh, DoF numbering, partition); no GPU needed.
+#include <cstring>
+
+#include "../../include/nsb.h"
+#include "nsb_host.hpp"
+
+struct nsh_mesh_s { nsb::Mesh M; };
+struct nsh_dofs_s { nsb::Dofs D; };
+
+extern "C" {
+
+nsh_mesh nsh_mesh_cylinder2d(int s)
+{
+  if (s < 1) return nullptr;
+  auto *m = new nsh_mesh_s();
+  m->M = nsb::make_cylinder2d(s);
+  return m;
+}
+nsh_mesh nsh_mesh_cylinder3d(int s, int nz)
+{
+  if (s < 1 || nz < 1) return nullptr;
+  auto *m = new nsh_mesh_s();
+  m->M = nsb::make_cylinder3d(s, nz);
+  return m;
+}
+nsh_mesh nsh_mesh_cube(int n)
+{
+  if (n < 1) return nullptr;
+  auto *m = new nsh_mesh_s();
+  m->M = nsb::make_cube(n);
+  return m;
+}
+nsh_mesh nsh_mesh_box(int dim, int nx, int ny, int nz, const double *lo, const double *hi)
+{
+  if ((dim != 2 && dim != 3) || nx < 1 || ny < 1 || (dim == 3 && nz < 1) || !lo || !hi) return nullptr;
+  auto *m = new nsh_mesh_s();
+  m->M = nsb::make_box(dim, nx, ny, nz, lo, hi);
+  return m;
+}
+nsh_mesh nsh_mesh_read_msh(const char *path)
+{
+  auto *m = new nsh_mesh_s();
+  std::string err;
+  if (!path || !nsb::read_msh(path, m->M, err)) { delete m; return nullptr; }
+  return m;
+}
+int nsh_mesh_write_msh(nsh_mesh m, const char *path)
+{
+  if (!m || !path) return NSB_ERR_ARG;
+  return nsb::write_msh(m->M, path) ? NSB_OK : NSB_ERR_IO;
+}
+void nsh_mesh_free(nsh_mesh m) { delete m; }
+int nsh_mesh_dim(nsh_mesh m) { return m ? m->M.dim : 0; }
+int32_t nsh_mesh_n_vertices(nsh_mesh m) { return m ? int32_t(m->M.n_vertices()) : 0; }
+int32_t nsh_mesh_n_cells(nsh_mesh m) { return m ? int32_t(m->M.n_cells()) : 0; }
+int32_t nsh_mesh_n_bfaces(nsh_mesh m) { return m ? int32_t(m->M.bids.size()) : 0; }
+const double *nsh_mesh_vertices(nsh_mesh m) { return m ? m->M.verts.data() : nullptr; }
+const int32_t *nsh_mesh_cells(nsh_mesh m) { return m ? m->M.cells.data() : nullptr; }
+const int32_t *nsh_mesh_bfaces(nsh_mesh m) { return m ? m->M.bfaces.data() : nullptr; }
+const int32_t *nsh_mesh_bface_ids(nsh_mesh m) { return m ? m->M.bids.data() : nullptr; }
+const int32_t *nsh_mesh_bface_cells(nsh_mesh m) { return m ? m->M.bcell.data() : nullptr; }
+int nsh_mesh_reorder_cells(nsh_mesh m, int mode, int block)
+{
+  if (!m || mode < 0 || mode > 2 || block < 1) return NSB_ERR_ARG;
+  m->M.reorder_cells(mode, block);
+  return NSB_OK;
+}
+
+nsh_dofs nsh_dofs_create(nsh_mesh m)
+{
+  if (!m) return nullptr;
+  auto *d = new nsh_dofs_s();
+  nsb::number_dofs(m->M, d->D);
+  return d;
+}
+void nsh_dofs_free(nsh_dofs d) { delete d; }
+int32_t nsh_dofs_n_nodes(nsh_dofs d) { return d ? d->D.n_nodes : 0; }
+int32_t nsh_dofs_n_p(nsh_dofs d) { return d ? d->D.n_p : 0; }
+int32_t nsh_dofs_per_cell(nsh_dofs d) { return d ? d->D.dpc : 0; }
+const int32_t *nsh_dofs_cell_dofs(nsh_dofs d) { return d ? d->D.cell_dofs.data() : nullptr; }
+const double *nsh_dofs_node_xyz(nsh_dofs d) { return d ? d->D.node_xyz.data() : nullptr; }
+const double *nsh_dofs_p_xyz(nsh_dofs d) { return d ? d->D.p_xyz.data() : nullptr; }
+const double *nsh_dofs_cell_coords(nsh_dofs d) { return d ? d->D.cell_coords.data() : nullptr; }
+
+int32_t nsh_dofs_boundary_nodes(nsh_dofs d, nsh_mesh m, const int32_t *ids, int32_t n_ids, int32_t *out)
+{
+  if (!d || !m) return -1;
+  const nsb::Mesh &M = m->M;
+  const nsb::Dofs &D = d->D;
+  std::vector<char> seen(D.n_nodes, 0);
+  int32_t n = 0;
+  for (size_t b = 0; b < M.bids.size(); ++b) {
+    bool want = false;
+    for (int k = 0; k < n_ids; ++k) want |= (ids[k] == M.bids[b]);
+    if (!want) continue;
+    int loc[6];
+    const int nl = nsb::face_local_nodes(D.dim, M.blocal[b], loc);
+    for (int k = 0; k < nl; ++k) {
+      const int node = D.cell_nodes[size_t(M.bcell[b]) * D.n2 + loc[k]];
+      if (!seen[node]) {
+        seen[node] = 1;
+        if (out) out[n] = node;
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+int32_t nsh_dofs_boundary_faces(nsh_dofs d, nsh_mesh m, int32_t id, int32_t *face_cell, int32_t *face_local)
+{
+  if (!d || !m) return -1;
+  const nsb::Mesh &M = m->M;
+  int32_t n = 0;
+  for (size_t b = 0; b < M.bids.size(); ++b)
+    if (M.bids[b] == id) {
+      if (face_cell) face_cell[n] = M.bcell[b];
+      if (face_local) face_local[n] = M.blocal[b];
+      ++n;
+    }
+  return n;
+}
+
+int nsh_partition_cells(nsh_mesh m, int nparts, int32_t *part)
+{
+  if (!m || nparts < 1 || !part) return NSB_ERR_ARG;
+  std::vector<int> p;
+  nsb::partition_cells_rcb(m->M, nparts, p);
+  std::memcpy(part, p.data(), sizeof(int) * p.size());
+  return NSB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,225 @@
+"""Parity of the CUDA hot path against the CPU oracle, called through the C ABI (`-m gpu`).
+
+Tolerances are the north_star's: assembled entries 1e-12 relative (to the row scale, SURVEY.md
+H7), fields 1e-8 relative L2 after each step.  Sizes are small enough for the oracle to finish
+in seconds; size-independent properties at full size are in test_gpu_properties.py.
+"""
+import numpy as np
+import pytest
+
+import helpers as T
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cyl2d", "box2d", "box3d", "cube", "cyl3d"]
+ENTRY_TOL = 1e-12
+FIELD_TOL = 1e-8
+
+
+def _setup(case_name, state_scale=0.3, time=4.0, **params):
+    case = T.Case(case_name)
+    rows, vals = case.bc(time)
+    o, e = case.oracle(), case.engine(**params)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    e.set_dirichlet_values(vals)
+    x0 = state_scale * case.random_state()
+    o.set_solution(x0)
+    e.set_solution(x0)
+    if case.variant == "conv":  # Neumann face term of Convergence3D.cpp:309-330
+        neu = case.neumann(0.0)
+        o.set_neumann_rhs(neu)
+        e.set_neumann_rhs(neu[: case.n_u])
+    return case, o, e
+
+
+@pytest.mark.parametrize("case_name", CASES)
+def test_sparsity_pattern_matches_reference_layout(case_name):
+    """a5: make_sparsity_pattern with the coupling table of NavierStokes2D.cpp:109-119."""
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine()
+    rp, ci, pm_rp, pm_ci = o.pattern4
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix((np.ones(len(ci)), ci, rp), shape=(case.N, case.N))
+    nu = case.n_u
+    for blk, M in (("F", A[:nu, :nu]), ("Bt", A[:nu, nu:]), ("B", A[nu:, :nu])):
+        erp, eci = e.pattern(blk)
+        assert T.same_pattern(M, erp, eci), blk
+        M = M.tocsr(); M.sort_indices()
+        e.check_pattern(blk, M.indptr, M.indices)  # the optional hand-in path accepts the reference pattern
+    erp, eci = e.pattern("Mp")
+    assert np.array_equal(erp, pm_rp) and np.array_equal(eci, pm_ci)
+    # a corrupted pattern must be refused
+    bad = eci.copy(); bad[0] += 1
+    with pytest.raises(Exception):
+        e.check_pattern("Mp", erp, bad)
+
+
+@pytest.mark.parametrize("case_name", CASES)
+def test_assemble_first_entries(case_name):
+    """a1: NavierStokes::assemble -- all five matrices and the rhs, entrywise."""
+    case, o, e = _setup(case_name)
+    o.assemble_first()
+    e.assemble_first()
+    for mat, oname in (("system", "sys"), ("mass", "mass"), ("stiffness", "stiff")):
+        ob = T.oracle_blocks(o, oname)
+        for blk in ("F", "Bt", "B"):
+            err = T.entry_error(e.matrix(mat, blk), ob[blk])
+            assert err < ENTRY_TOL, (mat, blk, err)
+    import scipy.sparse as sp
+
+    Mp_o = sp.csr_matrix((o.array("pmass", o.pm_nnz), o.pattern4[3], o.pattern4[2]), shape=(case.n_p, case.n_p))
+    assert T.entry_error(e.matrix("system", "Mp"), Mp_o) < ENTRY_TOL
+    rhs_o, rhs_e = o.array("rhs", case.N), e.get_rhs()
+    assert np.max(np.abs(rhs_e - rhs_o)) <= ENTRY_TOL * max(1.0, np.max(np.abs(rhs_o)))
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("case_name", CASES)
+def test_assemble_time_step_entries(case_name, kernel):
+    """a2 + a4: assemble_time_step (both kernels) incl. Dirichlet row clearing, over 2 steps."""
+    case, o, e = _setup(case_name, assembly_kernel=kernel)
+    o.assemble_first()
+    e.assemble_first()
+    rng = np.random.default_rng(7)
+    for step in range(2):
+        x = 0.5 * rng.uniform(-1, 1, case.N)
+        o.set_solution(x)
+        e.set_solution(x)
+        o.assemble_step()
+        e.assemble_step()
+        ob = T.oracle_blocks(o, "sys")
+        for blk in ("F", "Bt", "B"):
+            err = T.entry_error(e.matrix("system", blk), ob[blk])
+            assert err < ENTRY_TOL, (step, blk, err)
+        errc = T.entry_error(e.matrix("convection", "F"), T.oracle_blocks(o, "conv")["F"])
+        assert errc < ENTRY_TOL, errc
+        rhs_o, rhs_e = o.array("rhs", case.N), e.get_rhs()
+        assert np.max(np.abs(rhs_e - rhs_o)) <= ENTRY_TOL * max(1.0, np.max(np.abs(rhs_o)))
+
+
+@pytest.mark.parametrize("case_name", CASES)
+def test_dirichlet_replace_mode(case_name):
+    """a4: the alternative 'replace diagonal by dbar' reading of apply_boundary_values."""
+    case, o, e = _setup(case_name, dirichlet_mode=1)
+    o.set_options(dirichlet_mode=1)
+    o.assemble_first()
+    e.assemble_first()
+    assert T.entry_error(e.matrix("system", "F"), T.oracle_blocks(o, "sys")["F"]) < ENTRY_TOL
+    assert np.max(np.abs(e.get_rhs() - o.array("rhs", case.N))) <= ENTRY_TOL * max(1.0, np.max(np.abs(o.array("rhs", case.N))))
+
+
+@pytest.mark.parametrize("case_name", CASES)
+def test_spmv_blocks(case_name):
+    """a9 operator: BlockSparseMatrix::vmult and the block products used by the preconditioners."""
+    case, o, e = _setup(case_name)
+    o.assemble_first()
+    e.assemble_first()
+    o.precond_init(T.VARIANT_PREC[case.variant])
+    x = case.random_state()
+    yo, ye = o.system_vmult(x), e.system_vmult(x)
+    assert T.rel_l2(ye, yo) < 1e-13
+    xu, xp = x[: case.n_u], x[case.n_u:]
+    assert T.rel_l2(e.block_vmult("F", xu), o.block_vmult(0, xu, case.n_u)) < 1e-13
+    assert T.rel_l2(e.block_vmult("Bt", xp), o.block_vmult(1, xp, case.n_u)) < 1e-13
+    assert T.rel_l2(e.block_vmult("B", xu), o.block_vmult(2, xu, case.n_p)) < 1e-13
+
+
+@pytest.mark.parametrize("ptype", ["asimple", "yosida", "simple", "ayosida"])
+@pytest.mark.parametrize("case_name", ["cyl2d", "box3d", "cube"])
+def test_preconditioner_setup(case_name, ptype):
+    """a7/a8/a10/a11: diag extraction, Schur product (mmult) and the two ILU(0) factorisations."""
+    case, o, e = _setup(case_name, precond_type=ptype)
+    o.assemble_first()
+    e.assemble_first()
+    o.precond_init(ptype)
+    e.precond_init()
+    So, Se = o.schur(), e.schur()
+    assert T.same_pattern(So, Se.indptr, Se.indices)
+    assert T.entry_error(Se, So) < ENTRY_TOL
+    x = case.random_state()
+    xu, xp = x[: case.n_u], x[case.n_u:]
+    assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-11
+    assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-11
+    assert T.rel_l2(e.block_vmult("S", xp), o.block_vmult(3, xp, case.n_p)) < 1e-12
+
+
+@pytest.mark.parametrize("ptype", ["asimple", "yosida", "simple", "ayosida"])
+@pytest.mark.parametrize("case_name", ["cyl2d", "box3d", "cube"])
+def test_preconditioner_vmult(case_name, ptype):
+    """a7/a8: one application of P^{-1} (inner GMRES/CG to rel 1e-2 with ILU(0))."""
+    case, o, e = _setup(case_name, precond_type=ptype)
+    o.assemble_first()
+    e.assemble_first()
+    o.precond_init(ptype)
+    e.precond_init()
+    src = case.random_state()
+    dst0 = 0.1 * np.random.default_rng(3).uniform(-1, 1, case.N)  # aSIMPLE uses dst as initial guess
+    yo = o.precond_vmult(ptype, src, dst0)
+    ye = e.precond_vmult(src, dst0)
+    assert e.stat("n_inner_F") == o.stat("n_inner_F")
+    assert e.stat("n_inner_S") == o.stat("n_inner_S")
+    assert T.rel_l2(ye, yo) < FIELD_TOL
+
+
+@pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box2d", "asimple"), ("box3d", "yosida"),
+                                             ("cube", "yosida"), ("cyl3d", "yosida"), ("cyl2d", "simple"),
+                                             ("box3d", "ayosida")])
+def test_time_steps_fields(case_name, ptype):
+    """a6: three full time steps (assemble | assemble_time_step -> solve_time_step): same outer
+    iteration counts and fields within 1e-8 relative L2 after each step."""
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine(precond_type=ptype)
+    rows, vals = case.bc(0.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    x0 = case.initial()
+    o.set_solution(x0)
+    e.set_solution(x0)
+    t = 0.0
+    for step in range(3):
+        t += case.dt
+        tb = t if case.variant == "conv" else 2.0 + t  # non-trivial inlet amplitude
+        rows, vals = case.bc(tb)
+        o.set_dirichlet_values(vals)
+        e.set_dirichlet_values(vals)
+        if case.variant == "conv":
+            neu = case.neumann(t - case.dt)  # function_h lags by one step (Convergence3D.cpp:747-750)
+            o.set_neumann_rhs(neu)
+            e.set_neumann_rhs(neu[: case.n_u])
+        if step == 0:
+            o.assemble_first(); e.assemble_first()
+        else:
+            o.assemble_step(); e.assemble_step()
+        rc, its_o, _ = o.solve_step(ptype)
+        its_e, _, _ = e.solve_step()
+        assert rc == 0
+        assert its_e == its_o, (step, its_e, its_o)
+        xo, xe = o.array("sol_owned", case.N), e.get_solution()
+        nu = case.n_u
+        assert T.rel_l2(xe[:nu], xo[:nu]) < FIELD_TOL, (step, "velocity")
+        assert np.linalg.norm(xe[nu:] - xo[nu:]) < FIELD_TOL * max(np.linalg.norm(xo[nu:]), np.linalg.norm(xo[:nu])), (step, "pressure")
+
+
+def test_bad_arguments_are_refused():
+    """Error behaviour of the boundary: negative return codes + message, no exceptions across the ABI."""
+    from navierstokes_project_nm4pde_b200._lib import NsbError
+
+    case = T.Case("box2d")
+    e = case.engine()
+    with pytest.raises(NsbError) as ei:
+        e.set_params(precond_type=7)  # reference: std::runtime_error("Invalid preconditioner type")
+    assert "Invalid preconditioner type" in str(ei.value)
+    with pytest.raises(NsbError):
+        e.set_dirichlet(np.array([0], np.int32))  # only one component of a node
+    with pytest.raises(NsbError):
+        e.solve_step()  # nothing assembled
+    cd = case.dofs.cell_dofs()
+    cc = case.dofs.cell_coords().copy()
+    cc[0, [0, 1]] = cc[0, [1, 0]]  # negative Jacobian
+    from navierstokes_project_nm4pde_b200 import Engine
+
+    e2 = Engine(2)
+    with pytest.raises(NsbError):
+        e2.set_mesh(cc, cd, case.n_u, case.n_p)
