@@ -47,7 +47,7 @@ void Mesh::fix_orientation()
 }
 
 // Faces with exactly one adjacent cell; ids from the classifier.
-void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &classify)
+void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &classify, bool split_locked)
 {
   const int nv1 = dim + 1;
   const int64_t nc = n_cells();
@@ -89,6 +89,54 @@ void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &c
     bcell.push_back(r.cell);
     blocal.push_back(r.lf);
   }
+  if (split_locked && split_boundary_locked_cells() > 0) build_boundary(classify, false);
+}
+
+// A cell whose edges ALL lie in boundary faces (a tetrahedron cutting off a box corner) leaves the
+// pressure DoF of its corner vertex without any unconstrained velocity neighbour once those
+// boundaries are Dirichlet: the Schur complement B D^-1 B^T then has a zero row and ILU(0) breaks
+// down.  Such cells are split at their centroid (faces untouched => still conforming).
+// Needs bfaces; the caller rebuilds the boundary afterwards.  Returns the number of split cells.
+int Mesh::split_boundary_locked_cells()
+{
+  const int nv1 = dim + 1;
+  std::unordered_map<uint64_t, char> bedge;
+  const size_t nb = bids.size();
+  for (size_t b = 0; b < nb; ++b) {
+    const int *v = &bfaces[b * dim];
+    if (dim == 2) bedge[key2(v[0], v[1])] = 1;
+    else { bedge[key2(v[0], v[1])] = 1; bedge[key2(v[1], v[2])] = 1; bedge[key2(v[0], v[2])] = 1; }
+  }
+  const int64_t nc = n_cells();
+  int n_split = 0;
+  std::vector<int> extra;
+  for (int64_t c = 0; c < nc; ++c) {
+    int *v = &cells[c * nv1];
+    bool locked = true;
+    for (int a = 0; a < nv1 && locked; ++a)
+      for (int b = a + 1; b < nv1; ++b)
+        if (!bedge.count(key2(v[a], v[b]))) { locked = false; break; }
+    if (!locked) continue;
+    const int nv = int(verts.size() / dim);
+    for (int d = 0; d < dim; ++d) {
+      double s = 0;
+      for (int k = 0; k < nv1; ++k) s += verts[size_t(v[k]) * dim + d];
+      verts.push_back(s / nv1);
+    }
+    int orig[4];
+    for (int k = 0; k < nv1; ++k) orig[k] = v[k];
+    // sub-cell k replaces vertex k by the centroid; the first one overwrites the cell in place
+    for (int k = 0; k < nv1; ++k) {
+      int sub[4];
+      for (int j = 0; j < nv1; ++j) sub[j] = (j == k) ? nv : orig[j];
+      if (k == 0) for (int j = 0; j < nv1; ++j) v[j] = sub[j];
+      else extra.insert(extra.end(), sub, sub + nv1);
+    }
+    ++n_split;
+  }
+  cells.insert(cells.end(), extra.begin(), extra.end());
+  if (n_split) fix_orientation();
+  return n_split;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -489,7 +537,7 @@ bool read_msh(const std::string &path, Mesh &M, std::string &err)
     std::vector<int> k(v, v + m.dim);
     auto it = face_id.find(k);
     return it == face_id.end() ? 0 : it->second; // deal.II default boundary id 0
-  });
+  }, false);
   return true;
 }
 

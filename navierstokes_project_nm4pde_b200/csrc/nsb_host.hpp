@@ -18,7 +18,8 @@ struct Mesh {
   int64_t n_cells() const { return dim ? int64_t(cells.size()) / (dim + 1) : 0; }
   int64_t n_vertices() const { return dim ? int64_t(verts.size()) / dim : 0; }
   void fix_orientation();
-  void build_boundary(const std::function<int(const Mesh &, const int *)> &classify);
+  void build_boundary(const std::function<int(const Mesh &, const int *)> &classify, bool split_locked = true);
+  int split_boundary_locked_cells();
   void reorder_cells(int mode, int block);
 };
 

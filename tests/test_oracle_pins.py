@@ -1,0 +1,400 @@
+"""Pins of the CPU oracle (CPU only).
+
+The reference ships no tests, golden vectors or fixtures: parity is
+unpinned by the reference, so the oracle is pinned here by independent mathematics:
+  * quadrature tables integrate monomials exactly up to their degree;
+  * element matrices on a sheared simplex equal the exact rational integrals (sympy);
+  * patch identities (stiffness row sums, total mass, divergence of constants);
+  * ILU(0), the Schur product and the Krylov solvers against dense / scipy restatements;
+  * Ethier-Steinman convergence orders of one time step (Convergence3D driver semantics).
+"""
+import math
+from fractions import Fraction
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import ns_ref as R
+
+
+# ------------------------------------------------------------------------------------------ quadrature
+@pytest.mark.parametrize("dim,rule,degree", [(2, "wv", 5), (3, "wv", 5), (2, "dealii93", 5), (3, "dealii93", 3)])
+def test_quadrature_exactness(dim, rule, degree):
+    xi, w = R.quadrature(dim, rule)
+    tol = 1e-11 if rule == "dealii93" and dim == 2 else 1e-14  # 9.3's 2D table has ~12 digits
+    import itertools
+
+    for powers in itertools.product(range(degree + 1), repeat=dim):
+        if sum(powers) > degree:
+            continue
+        exact = math.prod(math.factorial(p) for p in powers) / math.factorial(sum(powers) + dim)
+        val = float(np.sum(w * np.prod(xi ** np.array(powers), axis=1)))
+        assert abs(val - exact) < tol, (powers, val, exact)
+
+
+def test_quadrature_sizes():
+    assert len(R.quadrature(2, "wv")[1]) == 7 and len(R.quadrature(3, "wv")[1]) == 14
+    assert len(R.quadrature(2, "dealii93")[1]) == 7 and len(R.quadrature(3, "dealii93")[1]) == 10
+
+
+# ------------------------------------------------------------------------------------------ sympy-exact cell
+def _exact_cell(dim, verts, U, nu, dt, temam, conv_mult):
+    """Exact (rational) local matrices of one cell in the FESystem local ordering."""
+    import sympy as s
+
+    xs = s.symbols("x0:%d" % dim)
+    lam = [1 - sum(xs)] + list(xs)
+    edges = R.EDGES[dim]
+    phi = [l * (2 * l - 1) for l in lam] + [4 * lam[a] * lam[b] for a, b in edges]
+    psi = lam
+    V = s.Matrix(verts)
+    J = s.Matrix([[V[k + 1, r] - V[0, r] for k in range(dim)] for r in range(dim)])
+    Jinv, det = J.inv(), J.det()
+
+    def grad(f):  # physical gradient: J^{-T} grad_hat
+        gh = s.Matrix([s.diff(f, x) for x in xs])
+        return Jinv.T * gh
+
+    def integ(f):
+        p = s.Poly(s.expand(f), *xs)
+        tot = 0
+        for mon, coef in p.terms():
+            tot += coef * s.Mul(*[s.factorial(m) for m in mon]) / s.factorial(sum(mon) + dim)
+        return tot * det
+
+    comp, base = R.local_dof_table(dim)
+    dpc = len(comp)
+    n2 = len(phi)
+    gphi = [grad(f) for f in phi]
+    uh = [sum(s.Rational(U[a][c]) * phi[a] for a in range(n2)) for c in range(dim)]
+    divu = sum(sum(s.Rational(U[a][c]) * gphi[a][c] for a in range(n2)) for c in range(dim))
+    out = {k: s.zeros(dpc, dpc) for k in ("mass", "stiff", "conv", "sysB", "pmass")}
+    rhs = s.zeros(dpc, 1)
+    for i in range(dpc):
+        ci, bi = comp[i], base[i]
+        for j in range(dpc):
+            cj, bj = comp[j], base[j]
+            if ci < dim and cj < dim and ci == cj:
+                out["mass"][i, j] = integ(phi[bi] * phi[bj]) / dt
+                out["stiff"][i, j] = nu * integ(sum(gphi[bi][d] * gphi[bj][d] for d in range(dim)))
+                adv = sum(gphi[bj][d] * uh[d] for d in range(dim)) * phi[bi]
+                c = conv_mult * integ(adv)
+                if temam:
+                    c += integ(s.Rational(1, 2) * divu * phi[bi] * phi[bj])
+                out["conv"][i, j] = c
+            if ci < dim and cj == dim:
+                out["sysB"][i, j] = -integ(psi[bj] * gphi[bi][ci])
+            if ci == dim and cj < dim:
+                out["sysB"][i, j] = integ(psi[bi] * gphi[bj][cj])
+            if ci == dim and cj == dim:
+                out["pmass"][i, j] = integ(psi[bi] * psi[bj]) / nu
+        if ci < dim:
+            rhs[i] = integ(uh[ci] * phi[bi]) / dt
+    return {k: np.array(v.tolist(), dtype=float) for k, v in out.items()}, np.array(rhs.tolist(), dtype=float).ravel()
+
+
+@pytest.mark.parametrize("dim,variant", [(2, "2d"), (3, "3d"), (3, "conv")])
+def test_element_matrices_are_exact(dim, variant):
+    """One sheared cell; degree-5 quadrature integrates every term of the hot path exactly, so the
+    oracle must reproduce the rational integrals to round-off (first step and later steps)."""
+    if dim == 2:
+        verts = [[Fraction(1, 10), Fraction(1, 5)], [Fraction(13, 10), Fraction(2, 5)], [Fraction(3, 5), Fraction(3, 2)]]
+    else:
+        verts = [[Fraction(0), Fraction(1, 10), Fraction(1, 5)], [Fraction(6, 5), Fraction(1, 5), Fraction(0)],
+                 [Fraction(3, 10), Fraction(7, 5), Fraction(1, 10)], [Fraction(1, 5), Fraction(2, 5), Fraction(9, 10)]]
+    v = np.array([[float(c) for c in p] for p in verts])
+    cells = np.array([list(range(dim + 1))], dtype=np.int32)
+    num = R.number_dofs(dim, v, cells)
+    n2, dpc = num["n2"], num["dpc"]
+    rng = np.random.default_rng(R.SEED)
+    U = [[Fraction(int(rng.integers(-9, 10)), 7) for _ in range(dim)] for _ in range(n2)]
+    nu, dt = Fraction(1, 100), Fraction(1, 8)
+    o = R.Oracle(dim, variant, v, cells, num, R.system_pattern(num), float(nu), float(dt))
+    x = np.zeros(num["N"])
+    cn = num["cell_nodes"][0]
+    for a in range(n2):
+        for c in range(dim):
+            x[dim * cn[a] + c] = float(U[a][c])
+    o.set_solution(x)
+    o.assemble_first()
+    cd = num["cell_dofs"][0]
+    exact, rhs = _exact_cell(dim, verts, U, nu, dt, temam=True, conv_mult=2 if variant == "conv" else 1)
+
+    def local(name):
+        A = o.matrix(name).toarray()
+        return A[np.ix_(cd, cd)]
+
+    scale = lambda M: max(1.0, np.abs(M).max())
+    assert np.abs(local("mass") - exact["mass"]).max() < 1e-13 * scale(exact["mass"])
+    assert np.abs(local("stiff") - exact["stiff"]).max() < 1e-13 * scale(exact["stiff"])
+    assert np.abs(local("conv") - exact["conv"]).max() < 1e-13 * scale(exact["conv"])
+    sys_exact = exact["sysB"] + exact["mass"] + exact["conv"] + exact["stiff"]
+    assert np.abs(local("sys") - sys_exact).max() < 1e-13 * scale(sys_exact)
+    assert np.abs(o.array("rhs", num["N"])[cd] - rhs).max() < 1e-13 * scale(rhs)
+    pat = R.system_pattern(num)
+    pm = sp.csr_matrix((o.array("pmass", o.pm_nnz), pat[3], pat[2]), shape=(num["n_p"],) * 2).toarray()
+    pidx = [i for i in range(dpc) if R.local_dof_table(dim)[0][i] == dim]
+    pl = cd[pidx] - num["n_u"]
+    pe = exact["pmass"][np.ix_(pidx, pidx)]
+    assert np.abs(pm[np.ix_(pl, pl)] - pe).max() < 1e-12 * scale(pe)
+    # later steps: convection once; Temam only in the 2D and CONV variants (NavierStokes3D.cpp:456)
+    o.assemble_step()
+    exact2, rhs2 = _exact_cell(dim, verts, U, nu, dt, temam=(variant != "3d"), conv_mult=1)
+    assert np.abs(local("conv") - exact2["conv"]).max() < 1e-13 * scale(exact2["conv"])
+    sys2 = exact["sysB"] + exact["mass"] + exact2["conv"] + exact["stiff"]
+    assert np.abs(local("sys") - sys2).max() < 1e-12 * scale(sys2)
+    assert np.abs(o.array("rhs", num["N"])[cd] - rhs2).max() < 1e-13 * scale(rhs2)
+
+
+# ------------------------------------------------------------------------------------------ patch identities
+@pytest.mark.parametrize("dim", [2, 3])
+def test_patch_identities(dim):
+    verts, cells = (R.square_mesh(4, jitter=0.25) if dim == 2 else R.cube_mesh(2, jitter=0.2))
+    num = R.number_dofs(dim, verts, cells)
+    nu, dt = 1e-3, 0.01
+    o = R.Oracle(dim, "2d" if dim == 2 else "3d", verts, cells, num, R.system_pattern(num), nu, dt)
+    o.set_solution(np.zeros(num["N"]))
+    o.assemble_first()
+    n_u = num["n_u"]
+    A = o.matrix("stiff")[:n_u, :n_u]
+    M = o.matrix("mass")[:n_u, :n_u]
+    S = o.matrix("sys")
+    vol = 1.0 if dim == 2 else 8.0
+    assert np.abs(A @ np.ones(n_u)).max() < 1e-12  # gradients of constants vanish
+    assert abs(M.sum() - vol * dim / dt) < 1e-9 * vol * dim / dt  # sum_ij M_ij = dim |Omega| / dt
+    B = S[n_u:, :n_u]
+    # B * (constant velocity) = int psi_i div(c) = 0 for every pressure row
+    for c in range(dim):
+        e = np.zeros(n_u)
+        e[c::dim] = 1.0
+        assert np.abs(B @ e).max() < 1e-13
+    Bt = S[:n_u, n_u:]
+    assert abs(Bt + B.T).max() < 1e-15  # block (0,1) = -block(1,0)^T before boundary conditions
+    # convection with zero advecting field vanishes, so sys(0,0) = M + A
+    assert abs(S[:n_u, :n_u] - (M + A)).max() < 1e-12 * abs(M).max()
+
+
+def test_dirichlet_rows_follow_dealii_trilinos_path():
+    verts, cells = R.square_mesh(3)
+    num = R.number_dofs(2, verts, cells)
+    o = R.Oracle(2, "2d", verts, cells, num, R.system_pattern(num), 1e-3, 0.01)
+    o.set_solution(np.zeros(num["N"]))
+    rows = np.array([0, 1, 6, 7], np.int32)
+    vals = np.array([1.5, -2.0, 0.25, 0.0])
+    o.set_dirichlet(rows, vals)
+    o.assemble_first()
+    S = o.matrix("sys").toarray()
+    S0 = (o.matrix("mass") + o.matrix("stiff")).toarray()
+    rhs = o.array("rhs", num["N"])
+    for r, g in zip(rows, vals):
+        off = np.delete(S[r], r)
+        assert np.all(off == 0.0)  # row cleared incl. block (0,1); columns untouched
+        assert S[r, r] == S0[r, r]  # non-zero diagonal preserved (SparseMatrix::clear_row)
+        assert rhs[r] == g * S[r, r]
+    assert np.any(S[:, rows][num["n_u"]:, :] != 0.0)  # B keeps its columns at constrained DoFs
+    o2 = R.Oracle(2, "2d", verts, cells, num, R.system_pattern(num), 1e-3, 0.01)
+    o2.set_options(dirichlet_mode=1)
+    o2.set_solution(np.zeros(num["N"]))
+    o2.set_dirichlet(rows, vals)
+    o2.assemble_first()
+    S2 = o2.matrix("sys").toarray()
+    assert all(S2[r, r] == abs(S0[0, 0]) for r in rows)
+
+
+# ------------------------------------------------------------------------------------------ solver pieces
+def _dense_ilu0(A):
+    """Textbook IKJ ILU(0) on the pattern of A (dense arrays)."""
+    n = A.shape[0]
+    P = A != 0
+    LU = A.copy()
+    for i in range(1, n):
+        for k in range(i):
+            if not P[i, k]:
+                continue
+            LU[i, k] = LU[i, k] / LU[k, k]
+            for j in range(k + 1, n):
+                if P[i, j]:
+                    LU[i, j] -= LU[i, k] * LU[k, j]
+    return LU
+
+
+def _small_problem(variant="2d", ptype="asimple"):
+    dim = 2 if variant == "2d" else 3
+    verts, cells = (R.square_mesh(4, hi=(0.41, 0.41), jitter=0.2) if dim == 2 else R.cube_mesh(2, jitter=0.15))
+    num = R.number_dofs(dim, verts, cells)
+    o = R.Oracle(dim, variant, verts, cells, num, R.system_pattern(num), 1e-3 if variant != "conv" else 1e-2,
+                 0.01 if dim == 2 else 4e-4)
+    bf = R.boundary_faces(dim, cells)
+    lo, hi = verts.min(axis=0), verts.max(axis=0)
+
+    def fid(vs):  # inlet x = lo (id 0), open outlet x = hi (id 1), everything else wall (id 2)
+        x = verts[list(vs)][:, 0]
+        return 0 if np.all(np.abs(x - lo[0]) < 1e-12) else (1 if np.all(np.abs(x - hi[0]) < 1e-12) else 2)
+
+    ids = [fid(vs) for (_, _, vs) in bf]
+    nodes = R.dirichlet_nodes(num, bf, ids, {0, 2})
+    rng = np.random.default_rng(5)
+    rows = (dim * nodes[:, None] + np.arange(dim)[None, :]).ravel()
+    o.set_dirichlet(rows, rng.uniform(-1, 1, rows.size))
+    o.set_solution(0.2 * rng.uniform(-1, 1, num["N"]))
+    o.assemble_first()
+    return o, num
+
+
+def test_ilu0_matches_textbook_and_ifpack_storage():
+    o, num = _small_problem()
+    o.precond_init("asimple")
+    n_u = num["n_u"]
+    F = o.matrix("sys")[:n_u, :n_u].toarray()
+    # the reference pattern holds explicit zeros (cross-component couplings): pattern from the CSR, not values
+    Fp = o.matrix("sys")[:n_u, :n_u].tocsr()
+    P = np.zeros_like(F, dtype=bool)
+    rows = np.repeat(np.arange(n_u), np.diff(Fp.indptr))
+    P[rows, Fp.indices] = True
+    LU = F.copy()
+    for i in range(1, n_u):
+        for k in np.nonzero(P[i, :i])[0]:
+            LU[i, k] /= LU[k, k]
+            cols = np.nonzero(P[i, k + 1:] & P[k, k + 1:])[0] + k + 1
+            LU[i, cols] -= LU[i, k] * LU[k, cols]
+    L = np.tril(LU, -1) + np.eye(n_u)
+    U = np.triu(LU)
+    x = np.random.default_rng(1).uniform(-1, 1, n_u)
+    y_ref = np.linalg.solve(U, np.linalg.solve(L, x))
+    y = o.ilu_apply(0, x)
+    assert np.linalg.norm(y - y_ref) < 1e-11 * np.linalg.norm(y_ref)
+
+
+def test_schur_product_matches_scipy():
+    for ptype in ("asimple", "yosida", "ayosida"):
+        o, num = _small_problem()
+        o.precond_init(ptype)
+        n_u = num["n_u"]
+        S = o.matrix("sys")
+        B, Bt, F = S[n_u:, :n_u], S[:n_u, n_u:], S[:n_u, :n_u]
+        M = o.matrix("mass")[:n_u, :n_u]
+        if ptype == "asimple":
+            d = -1.0 / F.diagonal()
+        elif ptype == "yosida":
+            d = -1.0 / M.diagonal()
+        else:
+            d = -1.0 / np.asarray(abs(M).sum(axis=1)).ravel()
+        ref = (B @ sp.diags(d) @ Bt).toarray()
+        got = o.schur().toarray()
+        assert np.abs(got - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("variant,ptype", [("2d", "asimple"), ("2d", "simple"), ("3d", "yosida"), ("3d", "ayosida"),
+                                           ("conv", "yosida")])
+def test_outer_solve_meets_the_references_stopping_rule(variant, ptype):
+    """GMRES stops on the PRECONDITIONED residual <= 1e-4 absolute (NavierStokes2D.cpp:534-536);
+    the true residual is then small and the direct solution close."""
+    o, num = _small_problem(variant, ptype)
+    rc, its, res = o.solve_step(ptype)
+    assert rc == 0 and 0 < its < 200 and res <= 1e-4
+    hist = o.residual_history()
+    assert len(hist) == its + 1 and hist[-1] == res and np.all(hist[:-1] > 1e-4)
+    A, b = o.matrix("sys").tocsc(), o.array("rhs", num["N"])
+    x = o.array("sol_owned", num["N"])
+    x_direct = spla.spsolve(A, b)
+    n_u = num["n_u"]
+    assert np.linalg.norm(x[:n_u] - x_direct[:n_u]) < 5e-3 * max(1.0, np.linalg.norm(x_direct[:n_u]))
+
+
+def test_tight_tolerances_reach_the_direct_solution():
+    """H2 'tight mode': outer 1e-12, inner 1e-10 gives the algebraic solution to ~1e-9."""
+    o, num = _small_problem("2d", "asimple")
+    o.set_options(outer_tol=1e-11, inner_rtol=1e-10)
+    rc, its, res = o.solve_step("asimple")
+    assert rc == 0
+    A, b = o.matrix("sys").tocsc(), o.array("rhs", num["N"])
+    x, xd = o.array("sol_owned", num["N"]), spla.spsolve(A, b)
+    assert np.linalg.norm(x - xd) < 1e-8 * np.linalg.norm(xd)
+
+
+def test_block_jacobi_partition_changes_only_the_preconditioner():
+    """mpirun -n P semantics: ILU(0) drops couplings across subdomains (Ifpack overlap 0)."""
+    o, num = _small_problem("2d", "asimple")
+    rc1, its1, _ = o.solve_step("asimple")
+    x1 = o.array("sol_owned", num["N"])
+    o2, _ = _small_problem("2d", "asimple")
+    part = np.zeros(num["N"], np.int32)
+    xy = np.concatenate([np.repeat(num["node_xyz"][:, 0], 2), num["p_xyz"][:, 0]])
+    part[xy > 0.2] = 1
+    o2.set_partition(part)
+    rc2, its2, _ = o2.solve_step("asimple")
+    x2 = o2.array("sol_owned", num["N"])
+    assert rc1 == 0 and rc2 == 0
+    assert np.linalg.norm(x1 - x2) < 1e-2 * max(1.0, np.linalg.norm(x1))  # both within the loose stopping rule
+
+
+# ------------------------------------------------------------------------------------------ convergence driver
+def _errors(num, verts, cells, x, t):
+    """VectorTools::integrate_difference semantics of Convergence3D.cpp:766-794 (velocity only)."""
+    xi, w = R.quadrature(3, "wv")
+    phi = np.zeros((10, len(w))); dphi = np.zeros((10, len(w), 3)); psi = np.zeros((4, len(w)))
+    import ctypes as C
+
+    R.lib().nso_tabulate(3, len(w), xi.ctypes.data_as(C.POINTER(C.c_double)), phi.ctypes.data_as(C.POINTER(C.c_double)),
+                         dphi.ctypes.data_as(C.POINTER(C.c_double)), psi.ctypes.data_as(C.POINTER(C.c_double)), None)
+    from navierstokes_project_nm4pde_b200 import problem as P
+
+    e2 = h2 = 0.0
+    for c in range(cells.shape[0]):
+        X = verts[cells[c]]
+        J = (X[1:] - X[0]).T
+        Jinv, det = np.linalg.inv(J), abs(np.linalg.det(J))
+        xq = X[0] + xi @ J.T
+        U = x[: num["n_u"]].reshape(-1, 3)[num["cell_nodes"][c]]  # [10,3]
+        uh = phi.T @ U
+        gh = np.einsum("aqk,kd,ac->qcd", dphi, Jinv, U)
+        ue, _ = P.exact_solution(xq, t)
+        ge = P.exact_gradient(xq, t)
+        e2 += float(np.sum(w * det * np.sum((uh - ue) ** 2, axis=1)))
+        h2 += float(np.sum(w * det * np.sum((gh - ge) ** 2, axis=(1, 2))))
+    return math.sqrt(e2), math.sqrt(e2 + h2)
+
+
+@pytest.mark.parametrize("neumann_face_ok", [True])
+def test_ethier_steinman_orders(neumann_face_ok):
+    """Convergence3D driver: one step dt = 4e-4, error against the exact field; P2 velocity gives
+    L2 ~ h^3, H1 ~ h^2.  Also fixes which cube face carries id 3 (Neumann, normal +y): with the
+    datum of Convergence3D.hpp:159-175 the orders are only reached on the y = +1 face."""
+    from navierstokes_project_nm4pde_b200 import problem as P
+
+    errs = []
+    for n in (2, 4):
+        verts, cells = R.cube_mesh(n)
+        num = R.number_dofs(3, verts, cells)
+        dt = 4e-4
+        o = R.Oracle(3, "conv", verts, cells, num, R.system_pattern(num), 1e-2, dt)
+        bf = R.boundary_faces(3, cells)
+
+        def fid(vs):
+            Pv = verts[list(vs)]
+            for ax in range(3):
+                if np.all(np.abs(Pv[:, ax] + 1) < 1e-12):
+                    return 2 * ax
+                if np.all(np.abs(Pv[:, ax] - 1) < 1e-12):
+                    return 2 * ax + 1
+
+        ids = [fid(vs) for (_, _, vs) in bf]
+        nodes = R.dirichlet_nodes(num, bf, ids, {0, 1, 2, 4, 5})
+        rows = (3 * nodes[:, None] + np.arange(3)[None, :]).ravel()
+        u, _ = P.exact_solution(num["node_xyz"][nodes], dt)
+        o.set_dirichlet(rows, u.ravel())
+        u0, _ = P.exact_solution(num["node_xyz"], 0.0)
+        _, p0 = P.exact_solution(num["p_xyz"], 0.0)
+        o.set_solution(np.concatenate([u0.ravel(), p0]))
+        o.set_neumann_rhs(R.neumann_rhs(num, verts, bf, ids, 0.0))
+        o.set_options(outer_tol=1e-10, inner_rtol=1e-6)
+        o.assemble_first()
+        rc, its, _ = o.solve_step("yosida")
+        assert rc == 0
+        errs.append(_errors(num, verts, cells, o.array("sol_owned", num["N"]), dt))
+    rate_l2 = math.log2(errs[0][0] / errs[1][0])
+    rate_h1 = math.log2(errs[0][1] / errs[1][1])
+    assert 2.5 < rate_l2 < 3.6, (errs, rate_l2)
+    assert 1.6 < rate_h1 < 2.6, (errs, rate_h1)
