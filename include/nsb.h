@@ -82,7 +82,11 @@ typedef struct nsb_params {
   int32_t dirichlet_mode; /* 0: keep nonzero diagonal, rhs = g*a_ii (deal.II Trilinos path); 1: replace by dbar */
   int32_t assembly_kernel; /* 0: tensor-contracted (default), 1: quadrature-loop kernel */
   int32_t sptrsv_kernel;   /* 0: default for this build, 1: level-scheduled launches, 2: chunked persistent */
-  int32_t reserved[8];
+  int32_t ilu_ordering;    /* 0: natural local row order (Ifpack in the reference; replay mode),
+                              1: greedy multicolour ordering of the ILU(0) factors (throughput mode;
+                              a different but equally valid ILU(0), like a different mpirun -n P).
+                              Must be set before nsb_finalize_setup. */
+  int32_t reserved[7];
 } nsb_params;
 
 /* Fill *p with the reference's literals for the given variant. */
@@ -171,6 +175,9 @@ int nsb_op_ilu_apply(nsb_handle h, int which, const double *x, double *y);
 /* dst = P^{-1} src; dst_in (may be NULL = zeros) is the incoming content of dst, which
  * aSIMPLE uses as initial guess (include/Preconditioners.hpp:273) */
 int nsb_op_precond_vmult(nsb_handle h, const double *src, const double *dst_in, double *dst);
+/* Row ordering of the ILU(0) factors (which = 0: F_s over P2 nodes, 1: S over pressure DoFs):
+ * factor row k is matrix row order[k]; identity for ilu_ordering = 0. */
+int nsb_get_ilu_order(nsb_handle h, int which, int32_t *order);
 /* Schur complement values on the pattern of NSB_BLK_S */
 int nsb_get_schur_values(nsb_handle h, double *vals);
 
@@ -182,6 +189,10 @@ double nsb_stat(nsb_handle h, const char *name);
  * which: "spmv_system", "spmv_F", "spmv_S", "assemble_step", "ilu_F", "ilu_S", "dot", "axpy" */
 int nsb_bench_kernel(nsb_handle h, const char *which, int iters, int flush_l2, double *ms_per_launch,
                      double *bytes_per_launch);
+/* CUDA-event stopwatch on the handle's launching stream: start (which = 0) / stop (which = 1);
+ * nsb_timer_elapsed_ms synchronises on the stop event. */
+int nsb_timer_mark(nsb_handle h, int which);
+int nsb_timer_elapsed_ms(nsb_handle h, double *ms);
 /* number of this library's kernel launches since the last call with reset != 0 */
 int64_t nsb_launch_count(nsb_handle h, int reset);
 

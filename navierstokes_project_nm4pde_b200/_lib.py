@@ -21,7 +21,7 @@ class NsbParams(C.Structure):
         ("gmres_tmp", C.c_int32), ("outer_maxit", C.c_int32), ("outer_tol", C.c_double),
         ("inner_maxit", C.c_int32), ("inner_rtol", C.c_double), ("alpha_simple", C.c_double),
         ("alpha_asimple", C.c_double), ("dirichlet_mode", C.c_int32), ("assembly_kernel", C.c_int32),
-        ("sptrsv_kernel", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("sptrsv_kernel", C.c_int32), ("ilu_ordering", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -59,9 +59,12 @@ SIGNATURES = {
     "nsb_op_ilu_apply": (C.c_int, [_H, C.c_int, c_double_p, c_double_p]),
     "nsb_op_precond_vmult": (C.c_int, [_H, c_double_p, c_double_p, c_double_p]),
     "nsb_get_schur_values": (C.c_int, [_H, c_double_p]),
+    "nsb_get_ilu_order": (C.c_int, [_H, C.c_int, c_int_p]),
     "nsb_stat": (C.c_double, [_H, C.c_char_p]),
     "nsb_bench_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "nsb_launch_count": (C.c_int64, [_H, C.c_int]),
+    "nsb_timer_mark": (C.c_int, [_H, C.c_int]),
+    "nsb_timer_elapsed_ms": (C.c_int, [_H, c_double_p]),
     # host prerequisites
     "nsh_mesh_cylinder2d": (_H, [C.c_int]),
     "nsh_mesh_cylinder3d": (_H, [C.c_int, C.c_int]),

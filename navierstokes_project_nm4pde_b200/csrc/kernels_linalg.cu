@@ -121,6 +121,7 @@ void spmv_F(Handle &H, const double *x_u, int goff_u, const double *x_p, int gof
                                                       H.Bt.val.p, x_p, H.n_p_owned, goff_p, y_u);
   NSB_CUDA(cudaGetLastError());
   H.launches++;
+  H.cnt_spmv_F++;
 }
 
 template <int DIM, int LPR>
@@ -166,6 +167,7 @@ void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u)
                                                        goff_p, y_u);
   NSB_CUDA(cudaGetLastError());
   H.launches++;
+  H.cnt_spmv_Bt++;
 }
 
 void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p)
@@ -182,6 +184,7 @@ void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p)
                                                       goff_u, y_p);
   NSB_CUDA(cudaGetLastError());
   H.launches++;
+  H.cnt_spmv_B++;
 }
 
 void spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p)
@@ -194,6 +197,7 @@ void spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p)
                                                    goff_p, y_p);
   NSB_CUDA(cudaGetLastError());
   H.launches++;
+  H.cnt_spmv_S++;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -399,34 +403,71 @@ static void level_schedule(int n, const std::vector<int> &rowptr, const std::vec
     for (int i = n - 1; i >= 0; --i) lvl_rows[pos[level[i]]++] = i;
 }
 
-void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs)
+// Greedy distance-1 colouring of the (structurally symmetric) owned-owned graph in natural row
+// order; the ILU ordering is "colour by colour, natural order inside a colour".
+static void multicolour_order(int n, const Csr &A, int n_owned_cols, std::vector<int> &order)
+{
+  std::vector<int> colour(n, -1), mark;
+  int ncol = 0;
+  for (int i = 0; i < n; ++i) {
+    mark.assign(ncol + 1, 0);
+    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+      const int j = A.colind[k];
+      if (j < n_owned_cols && j != i && colour[j] >= 0) mark[colour[j]] = 1;
+    }
+    int c = 0;
+    while (mark[c]) ++c;
+    colour[i] = c;
+    if (c == ncol) ++ncol;
+  }
+  std::vector<int> cnt(ncol + 1, 0);
+  for (int i = 0; i < n; ++i) cnt[colour[i] + 1]++;
+  for (int c = 0; c < ncol; ++c) cnt[c + 1] += cnt[c];
+  order.resize(n);
+  for (int i = 0; i < n; ++i) order[cnt[colour[i]]++] = i;
+}
+
+// ordering: 0 = natural local row order (what Ifpack does in the reference), 1 = multicolour.
+// The factor lives in the permuted index space: row k of the factor is row order[k] of A.
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering)
 {
   const int n = A.n_rows;
   ilu.n = n;
   ilu.bs_rhs = bs_rhs;
+  ilu.h_order.clear();
+  if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu.h_order);
+  else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
+  const std::vector<int> &order = ilu.h_order;
+  std::vector<int> pos(n_owned_cols > n ? n_owned_cols : n, -1);
+  for (int k = 0; k < n; ++k) pos[order[k]] = k;
   std::vector<int> rowptr(n + 1, 0), colind, src, diagpos(n, 0);
   colind.reserve(A.colind.size());
   src.reserve(A.colind.size());
-  for (int i = 0; i < n; ++i) {
+  std::vector<std::pair<int, int>> row;
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    row.clear();
     bool have_diag = false;
-    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-      const int j = A.colind[k];
-      if (j >= n_owned_cols) continue; // Ifpack_LocalFilter: off-process columns are dropped
+    for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+      const int j = A.colind[e];
+      if (j >= n_owned_cols || j >= n) continue; // Ifpack_LocalFilter: off-process columns are dropped
       if (j == i) have_diag = true;
-      colind.push_back(j);
-      src.push_back(k);
+      row.emplace_back(pos[j], e);
     }
     if (!have_diag) throw StateError("ILU: structurally missing diagonal");
-    rowptr[i + 1] = int(colind.size());
-    int dp = rowptr[i];
-    while (colind[dp] != i) ++dp;
-    diagpos[i] = dp;
+    std::sort(row.begin(), row.end());
+    for (auto &pe : row) { colind.push_back(pe.first); src.push_back(pe.second); }
+    rowptr[k + 1] = int(colind.size());
+    int dp = rowptr[k];
+    while (colind[dp] != k) ++dp;
+    diagpos[k] = dp;
   }
   ilu.nnz = int64_t(colind.size());
   ilu.rowptr.upload(rowptr);
   ilu.colind.upload(colind);
   ilu.src.upload(src);
   ilu.diagpos.upload(diagpos);
+  ilu.order.upload(ilu.h_order);
   ilu.val.alloc(colind.size());
   ilu.dinv.alloc(n);
   std::vector<int> rows;
@@ -435,6 +476,21 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   level_schedule(n, rowptr, colind, false, ilu.lvl_ptr_b, rows);
   ilu.lvl_rows_b.upload(rows);
   (void)H;
+}
+
+template <int BS>
+__global__ void k_perm_gather(int n, const int *__restrict__ order, const double *__restrict__ x,
+                              double *__restrict__ xp)
+{ // xp[k] = x[order[k]]
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * BS; t += gridDim.x * blockDim.x)
+    xp[t] = x[int64_t(BS) * order[t / BS] + (t % BS)];
+}
+template <int BS>
+__global__ void k_perm_scatter(int n, const int *__restrict__ order, const double *__restrict__ yp,
+                               double *__restrict__ y)
+{ // y[order[k]] = yp[k]
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * BS; t += gridDim.x * blockDim.x)
+    y[int64_t(BS) * order[t / BS] + (t % BS)] = yp[t];
 }
 
 __global__ void k_gather(int64_t n, const int *__restrict__ src, const double *__restrict__ a, double *__restrict__ out)
@@ -589,6 +645,7 @@ static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
 {
   if (ilu.n == 0) return;
+  (&ilu == &H.iluF ? H.cnt_ilu_F : H.cnt_ilu_S)++;
   const int nvals = ilu.n * ilu.bs_rhs;
   cudaStream_t s = H.stream;
   if (!ilu.graph_f) {
@@ -604,9 +661,15 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;
   }
-  NSB_CUDA(cudaMemcpyAsync(ilu.graph_x, x, sizeof(double) * size_t(nvals), cudaMemcpyDeviceToDevice, s));
+  const unsigned pg = vgrid(nvals);
+  if (ilu.bs_rhs == 1) k_perm_gather<1><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, x, ilu.graph_x);
+  else if (ilu.bs_rhs == 2) k_perm_gather<2><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, x, ilu.graph_x);
+  else k_perm_gather<3><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, x, ilu.graph_x);
   NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
-  NSB_CUDA(cudaMemcpyAsync(y, ilu.graph_x, sizeof(double) * size_t(nvals), cudaMemcpyDeviceToDevice, s));
+  if (ilu.bs_rhs == 1) k_perm_scatter<1><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, ilu.graph_x, y);
+  else if (ilu.bs_rhs == 2) k_perm_scatter<2><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, ilu.graph_x, y);
+  else k_perm_scatter<3><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, ilu.graph_x, y);
+  H.launches += 2;
   H.launches += (int64_t(ilu.lvl_ptr_f.size()) - 2 > 0 ? int64_t(ilu.lvl_ptr_f.size()) - 2 : 0) +
                 (int64_t(ilu.lvl_ptr_b.size()) - 1);
 }

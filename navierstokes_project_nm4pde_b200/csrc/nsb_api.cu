@@ -24,6 +24,8 @@ Handle::~Handle()
     if (ilu->graph_f) cudaGraphExecDestroy(ilu->graph_f);
     if (ilu->graph_x) cudaFree(ilu->graph_x);
   }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
   if (h_pinned) cudaFreeHost(h_pinned);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -100,6 +102,8 @@ extern "C" int nsb_create(nsb_handle *out, int dim, int device_id, int nranks, i
     nsb_default_params(&H.prm, dim == 2 ? NSB_VARIANT_2D : NSB_VARIANT_3D);
     NSB_CUDA(cudaStreamCreateWithFlags(&H.stream, cudaStreamNonBlocking));
     NSB_CUDA(cudaMallocHost((void **)&H.h_pinned, sizeof(double) * 256));
+    NSB_CUDA(cudaEventCreate(&H.ev0));
+    NSB_CUDA(cudaEventCreate(&H.ev1));
     H.d_scratch.alloc(64 + 1024 + 8);
     H.d_scratch.zero();
     NSB_CUDA(cudaDeviceSynchronize());
@@ -128,6 +132,9 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
     if (!p) throw ArgError("nsb_set_params: null");
     if (p->precond_type < 0 || p->precond_type > 3) throw ArgError("Invalid preconditioner type");
     if (p->gmres_tmp < 3 || p->gmres_tmp > 200) throw ArgError("nsb_set_params: gmres_tmp out of range");
+    if (p->ilu_ordering < 0 || p->ilu_ordering > 1) throw ArgError("nsb_set_params: ilu_ordering must be 0 or 1");
+    if (H.finalized && p->ilu_ordering != H.prm.ilu_ordering)
+      throw StateError("nsb_set_params: ilu_ordering must be chosen before nsb_finalize_setup");
     if (!(p->deltat > 0) || !(p->nu > 0)) throw ArgError("nsb_set_params: nu and deltat must be positive");
     const bool realloc_ws = H.finalized && p->gmres_tmp != H.prm.gmres_tmp;
     const bool retensor = H.finalized && p->variant != H.prm.variant;
@@ -295,8 +302,12 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     H.d_neumann.alloc(size_t(H.nu_owned()));
     H.d_neumann.zero();
     // ILU(0) schedules (static pattern => symbolic work once)
-    ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim);
-    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1);
+    for (DevIlu *ilu : {&H.iluF, &H.iluS}) { // schedules are rebuilt: drop graphs captured for the old ones
+      if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
+      if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
+    }
+    ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering);
+    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering);
     solver_alloc(H);
     NSB_CUDA(cudaDeviceSynchronize());
     H.finalized = true;
@@ -532,6 +543,7 @@ static void do_solve(Handle &H, int32_t *outer_iters, double *t_prec, double *t_
 {
   if (!H.assembled) throw StateError("nsb_solve_step before assembly");
   H.n_inner_F = H.n_inner_S = H.n_F_solves = H.n_S_solves = H.n_vmult = 0;
+  H.cnt_spmv_F = H.cnt_spmv_S = H.cnt_spmv_B = H.cnt_spmv_Bt = H.cnt_ilu_F = H.cnt_ilu_S = H.cnt_dot = H.cnt_sync = 0;
   sync(H);
   const auto t0 = std::chrono::steady_clock::now();
   precond_init(H);
@@ -627,6 +639,15 @@ extern "C" int nsb_get_matrix_values(nsb_handle h, int mat, int blk, double *val
       NSB_CUDA(cudaMemcpy(vals, H.S.val.p, sizeof(double) * H.S.nnz, cudaMemcpyDeviceToHost));
     } else
       throw ArgError("unknown block id");
+  });
+}
+
+extern "C" int nsb_get_ilu_order(nsb_handle h, int which, int32_t *order)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!H.finalized) throw StateError("setup not finalized");
+    const DevIlu &ilu = which == 0 ? H.iluF : H.iluS;
+    std::memcpy(order, ilu.h_order.data(), sizeof(int) * ilu.h_order.size());
   });
 }
 
@@ -727,11 +748,35 @@ extern "C" double nsb_stat(nsb_handle h, const char *name)
   if (n == "n_nodes") return double(H.n_nodes);
   if (n == "n_p") return double(H.n_p);
   if (n == "n_cells") return double(H.nc);
+  if (n == "cnt_spmv_F") return double(H.cnt_spmv_F);
+  if (n == "cnt_spmv_S") return double(H.cnt_spmv_S);
+  if (n == "cnt_spmv_B") return double(H.cnt_spmv_B);
+  if (n == "cnt_spmv_Bt") return double(H.cnt_spmv_Bt);
+  if (n == "cnt_ilu_F") return double(H.cnt_ilu_F);
+  if (n == "cnt_ilu_S") return double(H.cnt_ilu_S);
+  if (n == "cnt_dot") return double(H.cnt_dot);
+  if (n == "cnt_sync") return double(H.cnt_sync);
+  if (n == "nnz_iluF") return double(H.iluF.nnz);
+  if (n == "nnz_iluS") return double(H.iluS.nnz);
   if (n == "levels_F_fwd") return double(H.iluF.lvl_ptr_f.size()) - 1;
   if (n == "levels_F_bwd") return double(H.iluF.lvl_ptr_b.size()) - 1;
   if (n == "levels_S_fwd") return double(H.iluS.lvl_ptr_f.size()) - 1;
   if (n == "levels_S_bwd") return double(H.iluS.lvl_ptr_b.size()) - 1;
   return -1;
+}
+
+extern "C" int nsb_timer_mark(nsb_handle h, int which)
+{
+  return guarded(h, [&](Handle &H) { NSB_CUDA(cudaEventRecord(which == 0 ? H.ev0 : H.ev1, H.stream)); });
+}
+extern "C" int nsb_timer_elapsed_ms(nsb_handle h, double *ms)
+{
+  return guarded(h, [&](Handle &H) {
+    NSB_CUDA(cudaEventSynchronize(H.ev1));
+    float f = 0;
+    NSB_CUDA(cudaEventElapsedTime(&f, H.ev0, H.ev1));
+    if (ms) *ms = f;
+  });
 }
 
 extern "C" int64_t nsb_launch_count(nsb_handle h, int reset)

@@ -102,6 +102,8 @@ struct DevIlu {
   int64_t nnz = 0;
   DevBuf<int> rowptr, colind, diagpos; // diagpos[i]: first entry with col > i  (end of L part)
   DevBuf<int> src;                     // position of each entry in the source matrix
+  DevBuf<int> order;                   // factor row k = matrix row order[k]
+  std::vector<int> h_order;
   DevBuf<double> val, dinv;
   // forward (L / factorisation) and backward (U) level schedules
   std::vector<int> lvl_ptr_f, lvl_ptr_b;
@@ -194,6 +196,9 @@ struct Handle {
 
   // ---- statistics of the last solve
   long n_inner_F = 0, n_inner_S = 0, n_F_solves = 0, n_S_solves = 0, n_vmult = 0;
+  long cnt_spmv_F = 0, cnt_spmv_S = 0, cnt_spmv_B = 0, cnt_spmv_Bt = 0, cnt_ilu_F = 0, cnt_ilu_S = 0, cnt_dot = 0,
+       cnt_sync = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_outer = 0;
   double last_res = 0, t_assemble_ms = 0, t_prec_ms = 0, t_solve_ms = 0;
 
@@ -227,7 +232,7 @@ void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out
 // vv += sign * (*a_dev) * v_prev ; out_dev = vv . v_next      (SolverGMRES add_and_dot)
 void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
                          const double *v_next, double *out_dev);
-void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs);
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering);
 void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val);
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y); // y = U^-1 D^-1 L^-1 x
 void spgemm_schur(Handle &H); // S = B diag(negDinv) Bt on the static pattern

@@ -44,6 +44,7 @@ void reduce_fetch(Handle &H, double *dev, int n, double *host_out)
 {
   NSB_CUDA(cudaMemcpyAsync(H.h_pinned, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, H.stream));
   NSB_CUDA(cudaStreamSynchronize(H.stream));
+  H.cnt_sync++;
   for (int i = 0; i < n; ++i) host_out[i] = H.h_pinned[i];
 }
 
@@ -51,12 +52,14 @@ void reduce_fetch(Handle &H, double *dev, int n, double *host_out)
 static void dot_dev(Handle &H, int n, const double *x, const double *y, double *out)
 {
   vec_dot_dev(H, n, x, y, out);
+  H.cnt_dot++;
   if (H.nranks > 1) halo_allreduce(H, out, 1);
 }
 static void add_and_dot_dev(Handle &H, int n, double *vv, const double *a, double sign, const double *vp,
                             const double *vn, double *out)
 {
   vec_add_and_dot_dev(H, n, vv, a, sign, vp, vn, out);
+  H.cnt_dot++;
   if (H.nranks > 1) halo_allreduce(H, out, 1);
 }
 static double norm_host(Handle &H, int n, const double *x, double *slot)

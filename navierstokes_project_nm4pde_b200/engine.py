@@ -362,6 +362,12 @@ class Engine:
         self._ck(self.L.nsb_op_precond_vmult(self.h, dptr(src), di, dptr(dst)))
         return dst
 
+    def ilu_order(self, which):
+        n = (self.n_u_owned // self.dim) if which == 0 else self.n_p_owned
+        out = np.zeros(n, np.int32)
+        self._ck(self.L.nsb_get_ilu_order(self.h, which, iptr(out)))
+        return out
+
     def schur(self):
         import scipy.sparse as sp
 
@@ -378,6 +384,15 @@ class Engine:
         ms, nbytes = C.c_double(0), C.c_double(0)
         self._ck(self.L.nsb_bench_kernel(self.h, which.encode(), iters, 1 if flush_l2 else 0, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+    def timer_start(self):
+        self._ck(self.L.nsb_timer_mark(self.h, 0))
+
+    def timer_stop_ms(self):
+        self._ck(self.L.nsb_timer_mark(self.h, 1))
+        ms = C.c_double(0)
+        self._ck(self.L.nsb_timer_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self, reset=False):
         return int(self.L.nsb_launch_count(self.h, 1 if reset else 0))

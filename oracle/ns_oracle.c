@@ -160,6 +160,10 @@ typedef struct {
   csr_t L, U;      /* strictly lower (unit diag implied), strictly upper scaled by dinv */
   double *dinv;
   int n;
+  int nparts;      /* block-Jacobi subdomains (one MPI rank each in the reference) */
+  int *prow_ptr, *prows; /* rows of each part, ascending */
+  const int *order;      /* optional symmetric permutation: factor row k = matrix row order[k] */
+  double *xp, *yp;
 } ilu_t;
 
 typedef struct nso_ctx {
@@ -182,6 +186,7 @@ typedef struct nso_ctx {
   double visc, dt;
   int dirichlet_mode; /* 0: keep nonzero diagonal, rhs = g*a_ii (deal.II Trilinos path); 1: replace by dbar */
   int *part;          /* DoF -> subdomain (block-Jacobi ILU like mpirun -n P), NULL = 1 part */
+  int *order_u, *order_p; /* optional ILU orderings (performance mode of the engine), NULL = natural */
   /* solver settings */
   int gmres_tmp;            /* max_n_tmp_vectors, deal.II default 30 */
   double outer_tol;         /* 1e-4 absolute (src/NavierStokes2D.cpp:535) */
@@ -247,7 +252,7 @@ NSO_API nso_ctx *nso_create(int dim, int variant, int nc, const double *vcoords,
 
 static void ilu_free(ilu_t *f)
 {
-  csr_free(&f->L); csr_free(&f->U); free(f->dinv);
+  csr_free(&f->L); csr_free(&f->U); free(f->dinv); free(f->prow_ptr); free(f->prows); free(f->xp); free(f->yp);
   memset(f, 0, sizeof(*f));
 }
 
@@ -268,6 +273,7 @@ NSO_API void nso_destroy(nso_ctx *c)
   free(c->pm_rowptr); free(c->pm_colind); free(c->pm_val);
   free(c->rhs); free(c->sol); free(c->sol_owned); free(c->prev_sol);
   free(c->bc_rows); free(c->bc_vals); free(c->neumann); free(c->part); free(c->res_hist);
+  free(c->order_u); free(c->order_p);
   free(c);
 }
 
@@ -306,6 +312,14 @@ NSO_API void nso_set_solution(nso_ctx *c, const double *x)
   memcpy(c->sol_owned, x, (size_t)c->N * sizeof(double));
   memcpy(c->sol, x, (size_t)c->N * sizeof(double));
 }
+NSO_API void nso_set_ilu_order(nso_ctx *c, const int *order_u, const int *order_p)
+{
+  free(c->order_u); free(c->order_p);
+  c->order_u = c->order_p = NULL;
+  if (order_u) { c->order_u = (int *)xcalloc(c->nu, sizeof(int)); memcpy(c->order_u, order_u, sizeof(int) * c->nu); }
+  if (order_p) { c->order_p = (int *)xcalloc(c->np, sizeof(int)); memcpy(c->order_p, order_p, sizeof(int) * c->np); }
+}
+
 NSO_API void nso_set_partition(nso_ctx *c, const int *part)
 {
   free(c->part); c->part = NULL;
@@ -661,60 +675,127 @@ static void ilu_factor(const csr_t *A, const int *part, ilu_t *f)
       else f->dinv[i] = A->val[p];
     }
   }
-  /* Compute(): rows in natural local order; rows of different parts never interact */
-  int *colflag = (int *)xcalloc(n, sizeof(int));
-  for (int j = 0; j < n; ++j) colflag[j] = -1;
+  /* rows grouped by subdomain: different parts never interact (overlap 0), so they run in
+     parallel exactly like the ranks of `mpirun -n P` */
+  int nparts = 1;
+  if (part) for (int i = 0; i < n; ++i) if (part[i] + 1 > nparts) nparts = part[i] + 1;
+  f->nparts = nparts;
+  f->prow_ptr = (int *)xcalloc((size_t)nparts + 1, sizeof(int));
+  f->prows = (int *)xcalloc(n, sizeof(int));
+  for (int i = 0; i < n; ++i) f->prow_ptr[(part ? part[i] : 0) + 1]++;
+  for (int q = 0; q < nparts; ++q) f->prow_ptr[q + 1] += f->prow_ptr[q];
+  {
+    int *pos = (int *)xcalloc(nparts, sizeof(int));
+    for (int i = 0; i < n; ++i) { const int q = part ? part[i] : 0; f->prows[f->prow_ptr[q] + pos[q]++] = i; }
+    free(pos);
+  }
   int maxrow = 0;
   for (int i = 0; i < n; ++i) {
     int len = (f->L.rowptr[i + 1] - f->L.rowptr[i]) + (f->U.rowptr[i + 1] - f->U.rowptr[i]) + 1;
     if (len > maxrow) maxrow = len;
   }
-  int *InI = (int *)xcalloc((size_t)maxrow + 1, sizeof(int));
-  double *InV = (double *)xcalloc((size_t)maxrow + 1, sizeof(double));
   const double MinDiag = 2.2250738585072014e-308, MaxDiag = 1.0 / MinDiag;
-  for (int i = 0; i < n; ++i) {
-    const int NumL = f->L.rowptr[i + 1] - f->L.rowptr[i];
-    const int NumU = f->U.rowptr[i + 1] - f->U.rowptr[i];
-    for (int k = 0; k < NumL; ++k) { InI[k] = f->L.colind[f->L.rowptr[i] + k]; InV[k] = f->L.val[f->L.rowptr[i] + k]; }
-    InV[NumL] = f->dinv[i]; InI[NumL] = i;
-    for (int k = 0; k < NumU; ++k) { InI[NumL + 1 + k] = f->U.colind[f->U.rowptr[i] + k]; InV[NumL + 1 + k] = f->U.val[f->U.rowptr[i] + k]; }
-    const int NumIn = NumL + NumU + 1;
-    for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = k;
-    for (int jj = 0; jj < NumL; ++jj) {
-      const int j = InI[jj];
-      const double multiplier = InV[jj];
-      InV[jj] *= f->dinv[j];
-      for (int k = f->U.rowptr[j]; k < f->U.rowptr[j + 1]; ++k) {
-        const int kk = colflag[f->U.colind[k]];
-        if (kk > -1) InV[kk] -= multiplier * f->U.val[k];
+  /* Compute(): rows of a part in natural local order */
+#pragma omp parallel
+  {
+    int *colflag = (int *)xcalloc(n, sizeof(int));
+    for (int j = 0; j < n; ++j) colflag[j] = -1;
+    int *InI = (int *)xcalloc((size_t)maxrow + 1, sizeof(int));
+    double *InV = (double *)xcalloc((size_t)maxrow + 1, sizeof(double));
+#pragma omp for schedule(dynamic, 1)
+    for (int q = 0; q < nparts; ++q)
+      for (int r = f->prow_ptr[q]; r < f->prow_ptr[q + 1]; ++r) {
+        const int i = f->prows[r];
+        const int NumL = f->L.rowptr[i + 1] - f->L.rowptr[i];
+        const int NumU = f->U.rowptr[i + 1] - f->U.rowptr[i];
+        for (int k = 0; k < NumL; ++k) { InI[k] = f->L.colind[f->L.rowptr[i] + k]; InV[k] = f->L.val[f->L.rowptr[i] + k]; }
+        InV[NumL] = f->dinv[i]; InI[NumL] = i;
+        for (int k = 0; k < NumU; ++k) { InI[NumL + 1 + k] = f->U.colind[f->U.rowptr[i] + k]; InV[NumL + 1 + k] = f->U.val[f->U.rowptr[i] + k]; }
+        const int NumIn = NumL + NumU + 1;
+        for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = k;
+        for (int jj = 0; jj < NumL; ++jj) {
+          const int j = InI[jj];
+          const double multiplier = InV[jj];
+          InV[jj] *= f->dinv[j];
+          for (int k = f->U.rowptr[j]; k < f->U.rowptr[j + 1]; ++k) {
+            const int kk = colflag[f->U.colind[k]];
+            if (kk > -1) InV[kk] -= multiplier * f->U.val[k];
+          }
+        }
+        for (int k = 0; k < NumL; ++k) f->L.val[f->L.rowptr[i] + k] = InV[k];
+        double d = InV[NumL];
+        if (fabs(d) > MaxDiag) d = (d < 0) ? -MinDiag : MinDiag; else d = 1.0 / d;
+        f->dinv[i] = d;
+        for (int k = 0; k < NumU; ++k) f->U.val[f->U.rowptr[i] + k] = InV[NumL + 1 + k] * d;
+        for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = -1;
       }
-    }
-    for (int k = 0; k < NumL; ++k) f->L.val[f->L.rowptr[i] + k] = InV[k];
-    double d = InV[NumL];
-    if (fabs(d) > MaxDiag) d = (d < 0) ? -MinDiag : MinDiag; else d = 1.0 / d;
-    f->dinv[i] = d;
-    for (int k = 0; k < NumU; ++k) f->U.val[f->U.rowptr[i] + k] = InV[NumL + 1 + k] * d;
-    for (int k = 0; k < NumIn; ++k) colflag[InI[k]] = -1;
+    free(colflag); free(InI); free(InV);
   }
-  free(colflag); free(InI); free(InV);
 }
 
-/* y = U^{-1} D^{-1} L^{-1} x  (Ifpack_ILU::Solve) */
-static void ilu_apply(void *vf, const double *x, double *y)
+/* y = U^{-1} D^{-1} L^{-1} x  (Ifpack_ILU::Solve), subdomains in parallel */
+static void ilu_apply(void *vf, const double *x_in, double *y_out)
 {
   const ilu_t *f = (const ilu_t *)vf;
-  const int n = f->n;
-  for (int i = 0; i < n; ++i) {
-    double s = 0.0;
-    for (int k = f->L.rowptr[i]; k < f->L.rowptr[i + 1]; ++k) s += f->L.val[k] * y[f->L.colind[k]];
-    y[i] = x[i] - s;
+  const double *x = x_in;
+  double *y = y_out;
+  if (f->order) {
+    for (int k = 0; k < f->n; ++k) f->xp[k] = x_in[f->order[k]];
+    x = f->xp; y = f->yp;
   }
-  for (int i = 0; i < n; ++i) y[i] *= f->dinv[i];
-  for (int i = n - 1; i >= 0; --i) {
-    double s = 0.0;
-    for (int k = f->U.rowptr[i]; k < f->U.rowptr[i + 1]; ++k) s += f->U.val[k] * y[f->U.colind[k]];
-    y[i] = y[i] - s;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int q = 0; q < f->nparts; ++q) {
+    const int r0 = f->prow_ptr[q], r1 = f->prow_ptr[q + 1];
+    for (int r = r0; r < r1; ++r) {
+      const int i = f->prows[r];
+      double s = 0.0;
+      for (int k = f->L.rowptr[i]; k < f->L.rowptr[i + 1]; ++k) s += f->L.val[k] * y[f->L.colind[k]];
+      y[i] = x[i] - s;
+    }
+    for (int r = r0; r < r1; ++r) y[f->prows[r]] *= f->dinv[f->prows[r]];
+    for (int r = r1 - 1; r >= r0; --r) {
+      const int i = f->prows[r];
+      double s = 0.0;
+      for (int k = f->U.rowptr[i]; k < f->U.rowptr[i + 1]; ++k) s += f->U.val[k] * y[f->U.colind[k]];
+      y[i] = y[i] - s;
+    }
   }
+  if (f->order)
+    for (int k = 0; k < f->n; ++k) y_out[f->order[k]] = f->yp[k];
+}
+
+/* ILU(0) of P A P^T for the ordering `order` (row k of the permuted matrix = row order[k] of A) */
+static void ilu_factor_ordered(const csr_t *A, const int *part, const int *order, ilu_t *f)
+{
+  if (!order) { ilu_factor(A, part, f); return; }
+  const int n = A->n_rows;
+  int *inv = (int *)xcalloc(n, sizeof(int));
+  for (int k = 0; k < n; ++k) inv[order[k]] = k;
+  csr_t P;
+  P.n_rows = P.n_cols = n;
+  P.rowptr = (int *)xcalloc((size_t)n + 1, sizeof(int));
+  for (int k = 0; k < n; ++k) P.rowptr[k + 1] = P.rowptr[k] + (A->rowptr[order[k] + 1] - A->rowptr[order[k]]);
+  P.colind = (int *)xcalloc(P.rowptr[n], sizeof(int));
+  P.val = (double *)xcalloc(P.rowptr[n], sizeof(double));
+  int *ppart = part ? (int *)xcalloc(n, sizeof(int)) : NULL;
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    if (ppart) ppart[k] = part[i];
+    int o = P.rowptr[k];
+    for (int p = A->rowptr[i]; p < A->rowptr[i + 1]; ++p, ++o) { P.colind[o] = inv[A->colind[p]]; P.val[o] = A->val[p]; }
+    /* insertion sort by new column index */
+    for (int a = P.rowptr[k] + 1; a < P.rowptr[k + 1]; ++a) {
+      const int kc = P.colind[a]; const double kv = P.val[a];
+      int b = a - 1;
+      while (b >= P.rowptr[k] && P.colind[b] > kc) { P.colind[b + 1] = P.colind[b]; P.val[b + 1] = P.val[b]; --b; }
+      P.colind[b + 1] = kc; P.val[b + 1] = kv;
+    }
+  }
+  ilu_factor(&P, ppart, f);
+  f->order = order;
+  f->xp = (double *)xcalloc(n, sizeof(double));
+  f->yp = (double *)xcalloc(n, sizeof(double));
+  csr_free(&P); free(inv); free(ppart);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1127,8 +1208,8 @@ NSO_API int nso_precond_init(nso_ctx *c, int ptype)
   csr_mmult_diag(&c->B, c->negDinv, &c->Bt, &c->S); /* B->mmult(neg_S, *B_T, neg_diag_D_inv) */
   int *partS = NULL;
   if (c->part) partS = c->part + nu;
-  ilu_factor(&c->F, c->part, &c->iluF);
-  ilu_factor(&c->S, partS, &c->iluS);
+  ilu_factor_ordered(&c->F, c->part, c->order_u, &c->iluF);
+  ilu_factor_ordered(&c->S, partS, c->order_p, &c->iluS);
   return 0;
 }
 

@@ -447,6 +447,11 @@ class Oracle:
         part = np.ascontiguousarray(part, dtype=np.int32)
         self.L.nso_set_partition(self.h, _ip(part))
 
+    def set_ilu_order(self, order_u=None, order_p=None):
+        ou = None if order_u is None else np.ascontiguousarray(order_u, dtype=np.int32)
+        op = None if order_p is None else np.ascontiguousarray(order_p, dtype=np.int32)
+        self.L.nso_set_ilu_order(self.h, None if ou is None else _ip(ou), None if op is None else _ip(op))
+
     def assemble_first(self):
         self.L.nso_assemble_first(self.h)
 

@@ -223,3 +223,55 @@ def test_bad_arguments_are_refused():
     e2 = Engine(2)
     with pytest.raises(NsbError):
         e2.set_mesh(cc, cd, case.n_u, case.n_p)
+
+
+def _oracle_order(case, e):
+    """Hand the engine's ILU orderings to the oracle (F order is per P2 node -> all components)."""
+    ou = (case.dim * e.ilu_order(0)[:, None] + np.arange(case.dim)[None, :]).ravel()
+    return ou, e.ilu_order(1)
+
+
+@pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cube", "yosida"),
+                                             ("cyl3d", "yosida"), ("box2d", "simple"), ("box3d", "ayosida")])
+def test_multicolour_ilu_mode(case_name, ptype):
+    """Throughput mode (ilu_ordering = 1): ILU(0) of the multicolour-permuted matrices.  Same
+    checks as the replay mode, against the oracle factorising in the same ordering."""
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1)
+    ou, op = _oracle_order(case, e)
+    assert sorted(ou.tolist()) == list(range(case.n_u)) and sorted(op.tolist()) == list(range(case.n_p))
+    assert not np.array_equal(op, np.arange(case.n_p))
+    o.set_ilu_order(ou, op)
+    rows, vals = case.bc(0.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    x0 = case.initial()
+    o.set_solution(x0)
+    e.set_solution(x0)
+    t = 0.0
+    for step in range(3):
+        t += case.dt
+        rows, vals = case.bc(t if case.variant == "conv" else 2.0 + t)
+        o.set_dirichlet_values(vals)
+        e.set_dirichlet_values(vals)
+        if case.variant == "conv":
+            neu = case.neumann(t - case.dt)
+            o.set_neumann_rhs(neu)
+            e.set_neumann_rhs(neu[: case.n_u])
+        if step == 0:
+            o.assemble_first(); e.assemble_first()
+        else:
+            o.assemble_step(); e.assemble_step()
+        if step == 0:
+            o.precond_init(ptype); e.precond_init()
+            x = case.random_state()
+            xu, xp = x[: case.n_u], x[case.n_u:]
+            assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-11
+            assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-11
+        rc, its_o, _ = o.solve_step(ptype)
+        its_e, _, _ = e.solve_step()
+        assert rc == 0 and its_e == its_o, (step, its_e, its_o)
+        xo, xe = o.array("sol_owned", case.N), e.get_solution()
+        assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < FIELD_TOL, step
+    # far fewer dependency levels than the natural ordering
+    assert e.stat("levels_F_fwd") <= 40 and e.stat("levels_S_fwd") <= 80
