@@ -103,24 +103,62 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(int n_rows, const int *__
   if (sl == 0) y[row] = acc;
 }
 
+// 3D variant: one warp per node row, lane = d*8 + e (component d of entry e, lanes 24..31 idle).
+// The three lanes that share an entry read the three consecutive doubles of x, so the gather of
+// an entry costs ~1.5 L1 sectors instead of three separate 8-byte accesses (the L1/TEX pipe, not
+// DRAM, limited the sub-warp-per-row kernel: ncu profiles/r01).
+__global__ void __launch_bounds__(256) spmv_F3_kernel(int n_rows, const int *__restrict__ rowptr,
+                                                      const int *__restrict__ colind, const double *__restrict__ val,
+                                                      const double *__restrict__ xu, int n_nodes_owned, int goff_u,
+                                                      const int *__restrict__ bt_rowptr,
+                                                      const int *__restrict__ bt_colind,
+                                                      const double *__restrict__ bt_val, const double *__restrict__ xp,
+                                                      int n_p_owned, int goff_p, double *__restrict__ yu)
+{
+  const int lane = threadIdx.x & 31;
+  const int d = lane >> 3, e = lane & 7;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps_per_grid) {
+    double acc = 0.0;
+    if (d < 3) {
+      const int rs = rowptr[row], re = rowptr[row + 1];
+      int k = rs + e;
+      for (; k + 8 < re; k += 16) { // two independent gathers in flight
+        const int c0 = __ldcs(colind + k), c1 = __ldcs(colind + k + 8);
+        const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + 8);
+        const double x0 = xu[int64_t(3) * c0 + (c0 >= n_nodes_owned ? goff_u : 0) + d];
+        const double x1 = xu[int64_t(3) * c1 + (c1 >= n_nodes_owned ? goff_u : 0) + d];
+        acc += v0 * x0;
+        acc += v1 * x1;
+      }
+      if (k < re) {
+        const int c0 = __ldcs(colind + k);
+        acc += __ldcs(val + k) * xu[int64_t(3) * c0 + (c0 >= n_nodes_owned ? goff_u : 0) + d];
+      }
+      if (xp) {
+        const int e2 = bt_rowptr[row + 1];
+        for (int q = bt_rowptr[row] + e; q < e2; q += 8) {
+          const int c = bt_colind[q];
+          acc += bt_val[int64_t(q) * 3 + d] * xp[c + (c >= n_p_owned ? goff_p : 0)];
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (e == 0 && d < 3) yu[int64_t(3) * row + d] = acc;
+  }
+}
+
 static inline unsigned grid_for(int64_t threads, int block) { return unsigned((threads + block - 1) / block); }
+
+void spmv_Bt_acc(Handle &H, const double *x_p, int goff_p, double *y_u, bool accumulate);
 
 void spmv_F(Handle &H, const double *x_u, int goff_u, const double *x_p, int goff_p, double *y_u)
 {
-  const int n = H.n_nodes_owned;
-  if (n == 0) return;
-  constexpr int LPR = 8;
-  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
-  if (H.dim == 2)
-    spmv_F_kernel<2, LPR><<<grid, 256, 0, H.stream>>>(n, H.Fs.rowptr.p, H.Fs.colind.p, H.Fs.val.p, x_u,
-                                                      H.n_nodes_owned, goff_u, H.Bt.rowptr.p, H.Bt.colind.p,
-                                                      H.Bt.val.p, x_p, H.n_p_owned, goff_p, y_u);
-  else
-    spmv_F_kernel<3, LPR><<<grid, 256, 0, H.stream>>>(n, H.Fs.rowptr.p, H.Fs.colind.p, H.Fs.val.p, x_u,
-                                                      H.n_nodes_owned, goff_u, H.Bt.rowptr.p, H.Bt.colind.p,
-                                                      H.Bt.val.p, x_p, H.n_p_owned, goff_p, y_u);
-  NSB_CUDA(cudaGetLastError());
-  H.launches++;
+  if (H.n_nodes_owned == 0) return;
+  stream_spmv_F(H, x_u, goff_u, y_u);
+  if (x_p) spmv_Bt_acc(H, x_p, goff_p, y_u, true);
   H.cnt_spmv_F++;
 }
 
@@ -128,7 +166,7 @@ template <int DIM, int LPR>
 __global__ void __launch_bounds__(256) spmv_Bt_kernel(int n_rows, const int *__restrict__ bt_rowptr,
                                                       const int *__restrict__ bt_colind,
                                                       const double *__restrict__ bt_val, const double *__restrict__ xp,
-                                                      int n_p_owned, int goff_p, double *__restrict__ yu)
+                                                      int n_p_owned, int goff_p, double *__restrict__ yu, int accumulate)
 {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LPR, sl = tid % LPR;
@@ -149,11 +187,14 @@ __global__ void __launch_bounds__(256) spmv_Bt_kernel(int n_rows, const int *__r
     for (int d = 0; d < DIM; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, LPR);
   if (sl == 0) {
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) yu[int64_t(DIM) * row + d] = acc[d];
+    for (int d = 0; d < DIM; ++d) {
+      if (accumulate) yu[int64_t(DIM) * row + d] += acc[d];
+      else yu[int64_t(DIM) * row + d] = acc[d];
+    }
   }
 }
 
-void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u)
+void spmv_Bt_acc(Handle &H, const double *x_p, int goff_p, double *y_u, bool accumulate)
 {
   const int n = H.n_nodes_owned;
   if (n == 0) return;
@@ -161,14 +202,16 @@ void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u)
   const unsigned grid = grid_for(int64_t(n) * LPR, 256);
   if (H.dim == 2)
     spmv_Bt_kernel<2, LPR><<<grid, 256, 0, H.stream>>>(n, H.Bt.rowptr.p, H.Bt.colind.p, H.Bt.val.p, x_p, H.n_p_owned,
-                                                       goff_p, y_u);
+                                                       goff_p, y_u, accumulate ? 1 : 0);
   else
     spmv_Bt_kernel<3, LPR><<<grid, 256, 0, H.stream>>>(n, H.Bt.rowptr.p, H.Bt.colind.p, H.Bt.val.p, x_p, H.n_p_owned,
-                                                       goff_p, y_u);
+                                                       goff_p, y_u, accumulate ? 1 : 0);
   NSB_CUDA(cudaGetLastError());
   H.launches++;
   H.cnt_spmv_Bt++;
 }
+
+void spmv_Bt(Handle &H, const double *x_p, int goff_p, double *y_u) { spmv_Bt_acc(H, x_p, goff_p, y_u, false); }
 
 void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p)
 {
@@ -189,14 +232,8 @@ void spmv_B(Handle &H, const double *x_u, int goff_u, double *y_p)
 
 void spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p)
 {
-  const int n = H.n_p_owned;
-  if (n == 0) return;
-  constexpr int LPR = 16;
-  const unsigned grid = grid_for(int64_t(n) * LPR, 256);
-  spmv_csr_kernel<LPR><<<grid, 256, 0, H.stream>>>(n, H.S.rowptr.p, H.S.colind.p, H.S.val.p, x_p, H.n_p_owned,
-                                                   goff_p, y_p);
-  NSB_CUDA(cudaGetLastError());
-  H.launches++;
+  if (H.n_p_owned == 0) return;
+  stream_spmv_S(H, x_p, goff_p, y_p);
   H.cnt_spmv_S++;
 }
 
@@ -405,7 +442,8 @@ static void level_schedule(int n, const std::vector<int> &rowptr, const std::vec
 
 // Greedy distance-1 colouring of the (structurally symmetric) owned-owned graph in natural row
 // order; the ILU ordering is "colour by colour, natural order inside a colour".
-static void multicolour_order(int n, const Csr &A, int n_owned_cols, std::vector<int> &order)
+static void multicolour_order(int n, const Csr &A, int n_owned_cols, std::vector<int> &order,
+                              std::vector<int> &colour_ptr)
 {
   std::vector<int> colour(n, -1), mark;
   int ncol = 0;
@@ -423,6 +461,7 @@ static void multicolour_order(int n, const Csr &A, int n_owned_cols, std::vector
   std::vector<int> cnt(ncol + 1, 0);
   for (int i = 0; i < n; ++i) cnt[colour[i] + 1]++;
   for (int c = 0; c < ncol; ++c) cnt[c + 1] += cnt[c];
+  colour_ptr = cnt;
   order.resize(n);
   for (int i = 0; i < n; ++i) order[cnt[colour[i]]++] = i;
 }
@@ -435,7 +474,8 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   ilu.n = n;
   ilu.bs_rhs = bs_rhs;
   ilu.h_order.clear();
-  if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu.h_order);
+  std::vector<int> colour_ptr;
+  if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu.h_order, colour_ptr);
   else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
   const std::vector<int> &order = ilu.h_order;
   std::vector<int> pos(n_owned_cols > n ? n_owned_cols : n, -1);
@@ -471,11 +511,30 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   ilu.val.alloc(colind.size());
   ilu.dinv.alloc(n);
   std::vector<int> rows;
+  ilu.stream = false;
+  if (ordering == 1) {
+    // colours are a valid (contiguous) schedule in both directions: a row of colour c only
+    // couples with rows of other colours
+    rows.resize(n);
+    for (int k = 0; k < n; ++k) rows[k] = k;
+    ilu.lvl_ptr_f = colour_ptr;
+    ilu.lvl_rows_f.upload(rows);
+    const int nc = int(colour_ptr.size()) - 1;
+    ilu.lvl_ptr_b.assign(nc + 1, 0);
+    std::vector<int> rb;
+    rb.reserve(n);
+    for (int c = nc - 1; c >= 0; --c) {
+      for (int k = colour_ptr[c]; k < colour_ptr[c + 1]; ++k) rb.push_back(k);
+      ilu.lvl_ptr_b[nc - c] = int(rb.size());
+    }
+    ilu.lvl_rows_b.upload(rb);
+    stream_build_ilu(H, ilu, rowptr, colind, diagpos, colour_ptr);
+    return;
+  }
   level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);
   ilu.lvl_rows_f.upload(rows);
   level_schedule(n, rowptr, colind, false, ilu.lvl_ptr_b, rows);
   ilu.lvl_rows_b.upload(rows);
-  (void)H;
 }
 
 template <int BS>
@@ -552,6 +611,10 @@ void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val)
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());
+  if (ilu.sell) {
+    sell_fill(H, ilu.sellL, ilu.val.p);
+    sell_fill(H, ilu.sellU, ilu.val.p);
+  } else if (ilu.stream) stream_split_factors(H, ilu);
 }
 
 // Triangular solves, BS right-hand sides interleaved per row (BS = dim for F_s, 1 for S).
@@ -619,18 +682,96 @@ __global__ void __launch_bounds__(128) k_trsv_bwd_level(int n_rows_lvl, const in
   }
 }
 
+// 3-RHS variants with the lane = d*8 + e mapping (see spmv_F3_kernel); one warp per row.
+__global__ void __launch_bounds__(256) k_trsv_fwd_level3(int n_rows_lvl, const int *__restrict__ rows,
+                                                         const int *__restrict__ rowptr,
+                                                         const int *__restrict__ colind,
+                                                         const int *__restrict__ diagpos,
+                                                         const double *__restrict__ val, double *__restrict__ y)
+{
+  const int lane = threadIdx.x & 31;
+  const int d = lane >> 3, e = lane & 7;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_rows_lvl; w += warps_per_grid) {
+    const int i = rows[w];
+    double acc = 0.0;
+    if (d < 3) {
+      const int re = diagpos[i];
+      int k = rowptr[i] + e;
+      for (; k + 8 < re; k += 16) {
+        const int c0 = __ldcs(colind + k), c1 = __ldcs(colind + k + 8);
+        const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + 8);
+        acc += v0 * y[int64_t(3) * c0 + d];
+        acc += v1 * y[int64_t(3) * c1 + d];
+      }
+      if (k < re) acc += __ldcs(val + k) * y[int64_t(3) * __ldcs(colind + k) + d];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (e == 0 && d < 3) y[int64_t(3) * i + d] -= acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_trsv_bwd_level3(int n_rows_lvl, const int *__restrict__ rows,
+                                                         const int *__restrict__ rowptr,
+                                                         const int *__restrict__ colind,
+                                                         const int *__restrict__ diagpos,
+                                                         const double *__restrict__ val,
+                                                         const double *__restrict__ dinv, double *__restrict__ y)
+{
+  const int lane = threadIdx.x & 31;
+  const int d = lane >> 3, e = lane & 7;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_rows_lvl; w += warps_per_grid) {
+    const int i = rows[w];
+    double acc = 0.0;
+    if (d < 3) {
+      const int re = rowptr[i + 1];
+      int k = diagpos[i] + 1 + e;
+      for (; k + 8 < re; k += 16) {
+        const int c0 = __ldcs(colind + k), c1 = __ldcs(colind + k + 8);
+        const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + 8);
+        acc += v0 * y[int64_t(3) * c0 + d];
+        acc += v1 * y[int64_t(3) * c1 + d];
+      }
+      if (k < re) acc += __ldcs(val + k) * y[int64_t(3) * __ldcs(colind + k) + d];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (e == 0 && d < 3) y[int64_t(3) * i + d] = y[int64_t(3) * i + d] * dinv[i] - acc;
+  }
+}
+
 template <int BS>
 static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
 {
   constexpr int LPR = 8;
   const int nf = int(ilu.lvl_ptr_f.size()) - 1;
+  const int nb = int(ilu.lvl_ptr_b.size()) - 1;
+  if constexpr (BS == 3) {
+    for (int l = 1; l < nf; ++l) {
+      const int cnt = ilu.lvl_ptr_f[l + 1] - ilu.lvl_ptr_f[l];
+      const unsigned g = unsigned(std::min<int64_t>((int64_t(cnt) + 7) / 8, int64_t(kSM) * 64));
+      k_trsv_fwd_level3<<<g, 256, 0, s>>>(cnt, ilu.lvl_rows_f.p + ilu.lvl_ptr_f[l], ilu.rowptr.p, ilu.colind.p,
+                                         ilu.diagpos.p, ilu.val.p, y);
+    }
+    for (int l = 0; l < nb; ++l) {
+      const int cnt = ilu.lvl_ptr_b[l + 1] - ilu.lvl_ptr_b[l];
+      const unsigned g = unsigned(std::min<int64_t>((int64_t(cnt) + 7) / 8, int64_t(kSM) * 64));
+      k_trsv_bwd_level3<<<g, 256, 0, s>>>(cnt, ilu.lvl_rows_b.p + ilu.lvl_ptr_b[l], ilu.rowptr.p, ilu.colind.p,
+                                         ilu.diagpos.p, ilu.val.p, ilu.dinv.p, y);
+    }
+    H.launches += (nf > 0 ? nf - 1 : 0) + nb;
+    return;
+  } else {
   for (int l = 1; l < nf; ++l) { // level 0 rows have an empty L part
     const int cnt = ilu.lvl_ptr_f[l + 1] - ilu.lvl_ptr_f[l];
     k_trsv_fwd_level<BS, LPR><<<(cnt * LPR + 127) / 128, 128, 0, s>>>(cnt, ilu.lvl_rows_f.p + ilu.lvl_ptr_f[l],
                                                                      ilu.rowptr.p, ilu.colind.p, ilu.diagpos.p,
                                                                      ilu.val.p, y);
   }
-  const int nb = int(ilu.lvl_ptr_b.size()) - 1;
   for (int l = 0; l < nb; ++l) {
     const int cnt = ilu.lvl_ptr_b[l + 1] - ilu.lvl_ptr_b[l];
     k_trsv_bwd_level<BS, LPR><<<(cnt * LPR + 127) / 128, 128, 0, s>>>(cnt, ilu.lvl_rows_b.p + ilu.lvl_ptr_b[l],
@@ -638,6 +779,7 @@ static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
                                                                      ilu.val.p, ilu.dinv.p, y);
   }
   H.launches += (nf > 0 ? nf - 1 : 0) + nb;
+  }
 }
 
 // y = U^{-1} D^{-1} L^{-1} x.  The per-level launches are captured once into a CUDA graph that
@@ -649,17 +791,26 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
   const int nvals = ilu.n * ilu.bs_rhs;
   cudaStream_t s = H.stream;
   if (!ilu.graph_f) {
-    NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * size_t(nvals)));
+    NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * size_t(ilu.sell ? 4 * ilu.n : nvals)));
     cudaGraph_t g;
     const int64_t before = H.launches;
     NSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    if (ilu.bs_rhs == 1) trsv_levels<1>(H, ilu, ilu.graph_x, s);
+    if (ilu.sell) sell_trsv(H, ilu, ilu.graph_x, s);
+    else if (ilu.stream) stream_trsv(H, ilu, ilu.graph_x, s);
+    else if (ilu.bs_rhs == 1) trsv_levels<1>(H, ilu, ilu.graph_x, s);
     else if (ilu.bs_rhs == 2) trsv_levels<2>(H, ilu, ilu.graph_x, s);
     else trsv_levels<3>(H, ilu, ilu.graph_x, s);
     NSB_CUDA(cudaStreamEndCapture(s, &g));
     NSB_CUDA(cudaGraphInstantiate(&ilu.graph_f, g, 0));
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;
+  }
+  if (ilu.sell) {
+    sell_perm_in(H, ilu, x, ilu.graph_x);
+    NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
+    sell_perm_out(H, ilu, ilu.graph_x, y);
+    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1) - 1;
+    return;
   }
   const unsigned pg = vgrid(nvals);
   if (ilu.bs_rhs == 1) k_perm_gather<1><<<pg, 256, 0, s>>>(ilu.n, ilu.order.p, x, ilu.graph_x);

@@ -1,0 +1,243 @@
+// kernels_sell.cu -- sliced-ELL (SELL-32) kernels for the 3-component node graph: SpMV with F_s and
+// the colour-scheduled ILU(0) triangular solves.
+//
+// Why this format (ncu evidence in profiles/r01_*): every CSR variant tried on this matrix
+// (sub-warp per row, warp per row, shared-memory CSR-stream) ended either bound by the L1 data
+// pipe (l1tex__data_pipe_lsu_wavefronts ~80%: one wavefront per cycle per SM, >1.5 wavefronts
+// per stored entry) or by the dependent chain rowptr -> colind -> x with too few rows in flight.
+// SELL-32 fixes both:
+//   * one thread per row, 32 rows of similar length per slice stored column-major, so colind/val
+//     are read as perfectly coalesced 128 B / 256 B wavefronts (0.09 wavefronts per entry) and
+//     every lane has `len` independent gathers (2048 rows in flight per SM);
+//   * the gathered vector is kept in a padded 4-doubles-per-node staging array, so the three
+//     components of a node come with ONE 256-bit load (LDG.E.ENL2.256) instead of three 8-byte
+//     accesses;
+//   * no reduction at all (a row lives in one thread), entries are summed in column order.
+// Rows of one colour are mutually independent, so inside a colour they are sorted by length
+// (no padding waste) without changing the ILU(0) factors.
+#include <algorithm>
+#include <numeric>
+
+#include "nsb_internal.hpp"
+
+namespace nsb {
+
+constexpr int kSM = 148;
+
+__device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c)
+{
+  double d;
+  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// MODE 0: y[3r+d]  = sum            (SpMV, unpadded output)
+// MODE 1: y[4r+d] -= sum            (forward substitution of one colour; y is the padded staging)
+// MODE 2: y[4r+d]  = y*dinv - sum   (backward substitution of one colour)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__restrict__ slice_ptr,
+                                               const int *__restrict__ rowid, const int *__restrict__ col,
+                                               const double *__restrict__ val, const double *xp, double *y,
+                                               const double *__restrict__ dinv)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = s0 + warp; s < s1; s += nwarps) {
+    const int base = slice_ptr[s];
+    const int len = (slice_ptr[s + 1] - base) >> 5;
+    const int r = rowid[(int64_t(s) << 5) + lane];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const int *cp = col + base + lane;
+    const double *vp = val + base + lane;
+    // software pipeline: the colind/val loads of the next group of U entries are issued before the
+    // gathers of the current group, so one memory round trip covers U entries
+    constexpr int U = 4;
+    int c[U], nc[U];
+    double v[U], nv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = u < len;
+      c[u] = ok ? __ldcs(cp + u * 32) : 0;
+      v[u] = ok ? __ldcs(vp + u * 32) : 0.0;
+    }
+    for (int k = 0; k < len; k += U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = k + U + u < len;
+        nc[u] = ok ? __ldcs(cp + (k + U + u) * 32) : 0;
+        nv[u] = ok ? __ldcs(vp + (k + U + u) * 32) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double x0, x1, x2;
+        ld256(xp + 4 * int64_t(c[u]), x0, x1, x2);
+        a0 += v[u] * x0;
+        a1 += v[u] * x1;
+        a2 += v[u] * x2;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { c[u] = nc[u]; v[u] = nv[u]; }
+    }
+    if (r >= 0) {
+      if (MODE == 0) {
+        double *o = y + 3 * int64_t(r);
+        o[0] = a0; o[1] = a1; o[2] = a2;
+      } else {
+        double *o = y + 4 * int64_t(r);
+        if (MODE == 1) { o[0] -= a0; o[1] -= a1; o[2] -= a2; }
+        else { const double di = dinv[r]; o[0] = o[0] * di - a0; o[1] = o[1] * di - a1; o[2] = o[2] * di - a2; }
+      }
+    }
+  }
+}
+
+__global__ void k_sell_fill(int64_t n, const int *__restrict__ map, const double *__restrict__ src,
+                            double *__restrict__ val)
+{
+  for (int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; k < n; k += int64_t(gridDim.x) * blockDim.x) {
+    const int m = map[k];
+    val[k] = m >= 0 ? src[m] : 0.0;
+  }
+}
+
+// x (stride 3, ghosts at +goff) -> padded copy (stride 4)
+__global__ void k_pad3(int n_nodes, int n_owned, int goff, const double *__restrict__ x, double *__restrict__ xp)
+{
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes * 4; t += gridDim.x * blockDim.x) {
+    const int i = t >> 2, d = t & 3;
+    xp[t] = d < 3 ? x[int64_t(3) * i + (i >= n_owned ? goff : 0) + d] : 0.0;
+  }
+}
+// staging for the triangular solves: xp[4k+d] = x[3*order[k]+d] and back
+__global__ void k_perm_gather34(int n, const int *__restrict__ order, const double *__restrict__ x,
+                                double *__restrict__ xp)
+{
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 4; t += gridDim.x * blockDim.x) {
+    const int k = t >> 2, d = t & 3;
+    xp[t] = d < 3 ? x[int64_t(3) * order[k] + d] : 0.0;
+  }
+}
+__global__ void k_perm_scatter43(int n, const int *__restrict__ order, const double *__restrict__ yp,
+                                 double *__restrict__ y)
+{
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 3; t += gridDim.x * blockDim.x) {
+    const int k = t / 3, d = t - 3 * k;
+    y[int64_t(3) * order[k] + d] = yp[int64_t(4) * k + d];
+  }
+}
+
+// Build SELL-32 for the rows of `rowptr/colind`.  ranges: row ranges that must not share a slice
+// (colours); inside a range rows are sorted by length (descending) within windows of `window`
+// rows.  src[e]: index of CSR entry e in the value array the SELL values are filled from.
+void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
+                const std::vector<int> &ranges, int window, DevSell &out)
+{
+  std::vector<int> slice_ptr(1, 0), rowid, col, map;
+  out.range_slice.assign(ranges.size(), 0);
+  std::vector<int> rows;
+  for (size_t g = 0; g + 1 < ranges.size(); ++g) {
+    out.range_slice[g] = int(slice_ptr.size()) - 1;
+    const int a = ranges[g], b = ranges[g + 1];
+    rows.resize(b - a);
+    std::iota(rows.begin(), rows.end(), a);
+    for (int w0 = 0; w0 < b - a; w0 += window) {
+      const int w1 = std::min(b - a, w0 + window);
+      std::stable_sort(rows.begin() + w0, rows.begin() + w1, [&](int x, int y) {
+        return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+      });
+    }
+    for (int s = 0; s < b - a; s += 32) {
+      const int ns = std::min(32, b - a - s);
+      int len = 0;
+      for (int l = 0; l < ns; ++l) len = std::max(len, rowptr[rows[s + l] + 1] - rowptr[rows[s + l]]);
+      for (int l = 0; l < 32; ++l) rowid.push_back(l < ns ? rows[s + l] : -1);
+      const size_t base = col.size();
+      col.resize(base + size_t(len) * 32);
+      map.resize(base + size_t(len) * 32);
+      for (int l = 0; l < 32; ++l) {
+        const int r = l < ns ? rows[s + l] : -1;
+        const int rl = r >= 0 ? rowptr[r + 1] - rowptr[r] : 0;
+        const int pad_col = (r >= 0 && rl > 0) ? colind[rowptr[r]] : 0;
+        for (int k = 0; k < len; ++k) {
+          const size_t o = base + size_t(k) * 32 + l;
+          if (k < rl) { col[o] = colind[rowptr[r] + k]; map[o] = src.empty() ? rowptr[r] + k : src[rowptr[r] + k]; }
+          else { col[o] = pad_col; map[o] = -1; }
+        }
+      }
+      if (col.size() > size_t(0x7fffffff)) throw StateError("SELL: more than 2^31 slots");
+      slice_ptr.push_back(int(col.size()));
+    }
+  }
+  out.range_slice.back() = int(slice_ptr.size()) - 1;
+  out.n_slices = int(slice_ptr.size()) - 1;
+  out.n_slots = int64_t(col.size());
+  out.slice_ptr.upload(slice_ptr);
+  out.rowid.upload(rowid);
+  out.col.upload(col);
+  out.map.upload(map);
+  out.val.alloc(col.size());
+}
+
+void sell_fill(Handle &H, DevSell &S, const double *src)
+{
+  if (S.n_slots == 0) return;
+  k_sell_fill<<<unsigned(std::min<int64_t>((S.n_slots + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(S.n_slots, S.map.p,
+                                                                                                 src, S.val.p);
+  H.launches++;
+}
+
+static inline unsigned sell_grid(int n_slices)
+{
+  return unsigned(std::max(1, std::min((n_slices + 7) / 8, kSM * 8)));
+}
+
+// y_u = F_s x_u (3D).  x is copied once into the padded staging vector.
+void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u)
+{
+  if (H.sellF_dirty) {
+    sell_fill(H, H.sellF, H.Fs.val.p);
+    H.sellF_dirty = false;
+  }
+  const int nn = H.n_nodes;
+  k_pad3<<<unsigned(std::min((nn * 4 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(nn, H.n_nodes_owned, goff_u, x_u,
+                                                                                  H.d_xpad.p);
+  k_sell3<0><<<sell_grid(H.sellF.n_slices), 256, 0, H.stream>>>(0, H.sellF.n_slices, H.sellF.slice_ptr.p,
+                                                                H.sellF.rowid.p, H.sellF.col.p, H.sellF.val.p,
+                                                                H.d_xpad.p, y_u, nullptr);
+  NSB_CUDA(cudaGetLastError());
+  H.launches += 2;
+}
+
+// in-place triangular solves on the padded staging vector (permuted index space)
+void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
+{
+  const int nc = int(ilu.colour_ptr.size()) - 1;
+  for (int c = 1; c < nc; ++c) {
+    const int a = ilu.sellL.range_slice[c], b = ilu.sellL.range_slice[c + 1];
+    if (b <= a) continue;
+    k_sell3<1><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellL.slice_ptr.p, ilu.sellL.rowid.p, ilu.sellL.col.p,
+                                               ilu.sellL.val.p, yp, yp, nullptr);
+    H.launches++;
+  }
+  for (int c = nc - 1; c >= 0; --c) {
+    const int a = ilu.sellU.range_slice[c], b = ilu.sellU.range_slice[c + 1];
+    if (b <= a) continue;
+    k_sell3<2><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellU.slice_ptr.p, ilu.sellU.rowid.p, ilu.sellU.col.p,
+                                               ilu.sellU.val.p, yp, yp, ilu.dinv.p);
+    H.launches++;
+  }
+  NSB_CUDA(cudaGetLastError());
+}
+
+void sell_perm_in(Handle &H, DevIlu &ilu, const double *x, double *xp)
+{
+  k_perm_gather34<<<unsigned(std::min((ilu.n * 4 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(ilu.n, ilu.order.p, x, xp);
+  H.launches++;
+}
+void sell_perm_out(Handle &H, DevIlu &ilu, const double *yp, double *y)
+{
+  k_perm_scatter43<<<unsigned(std::min((ilu.n * 3 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(ilu.n, ilu.order.p, yp, y);
+  H.launches++;
+}
+
+} // namespace nsb

@@ -306,6 +306,13 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
       if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
       if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
     }
+    stream_build_spmv(H);
+    if (dim == 3) {
+      sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, H.sellF);
+      H.d_xpad.alloc(size_t(4) * H.n_nodes);
+      H.d_xpad.zero();
+    }
+    H.sellF_dirty = true;
     ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering);
     ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering);
     solver_alloc(H);
@@ -528,6 +535,7 @@ static void do_assemble_first(Handle &H)
   launch_assemble_first(H);
   mass_rows(H);
   launch_apply_dirichlet(H, true);
+  H.sellF_dirty = true;
   H.assembled = true;
   H.prec_ready = false;
 }
@@ -537,6 +545,7 @@ static void do_assemble_step(Handle &H)
   refresh_ghosts(H);
   launch_assemble_step(H, H.Fs.val.p);
   launch_apply_dirichlet(H, false);
+  H.sellF_dirty = true;
   H.prec_ready = false;
 }
 static void do_solve(Handle &H, int32_t *outer_iters, double *t_prec, double *t_solve)
@@ -852,6 +861,7 @@ extern "C" int nsb_bench_kernel(nsb_handle h, const char *which, int iters, int 
     if (bytes_per_launch) *bytes_per_launch = bytes;
     if (w == "assemble_step") { // restore a consistent system matrix
       launch_apply_dirichlet(H, false);
+      H.sellF_dirty = true;
       sync(H);
     }
   });

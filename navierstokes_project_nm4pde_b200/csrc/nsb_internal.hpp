@@ -94,6 +94,15 @@ struct DevCsr {
   }
 };
 
+// SELL-32 storage (kernels_sell.cu)
+struct DevSell {
+  int n_slices = 0;
+  int64_t n_slots = 0;
+  DevBuf<int> slice_ptr, rowid, col, map;
+  DevBuf<double> val;
+  std::vector<int> range_slice; // first slice of each row range (colour)
+};
+
 // ILU(0) factors in Ifpack's storage convention (strict lower part = a_ij * dinv_j, strict upper
 // part scaled by dinv_i, inverse diagonal separate), on the owned-columns pattern, plus the
 // level schedules of the two triangular solves.
@@ -105,6 +114,12 @@ struct DevIlu {
   DevBuf<int> order;                   // factor row k = matrix row order[k]
   std::vector<int> h_order;
   DevBuf<double> val, dinv;
+  // multicolour mode: split L / U factors and per-colour row blocks for the CSR-stream solves
+  bool stream = false, sell = false;
+  DevSell sellL, sellU;
+  DevBuf<int> Lp, Lc, Up, Uc, mapL, mapU, blkL, blkU;
+  DevBuf<double> Lv, Uv;
+  std::vector<int> colour_ptr, cblkL, cblkU;
   // forward (L / factorisation) and backward (U) level schedules
   std::vector<int> lvl_ptr_f, lvl_ptr_b;
   DevBuf<int> lvl_rows_f, lvl_rows_b;
@@ -164,6 +179,11 @@ struct Handle {
   DevBuf<double> d_C;             // convection (parity harness only, lazily allocated)
   DevCsr B, Bt, Mp, S;
   DevBuf<int> d_diagF;            // position of the diagonal in each F_s row
+  DevSell sellF;                  // F_s in SELL-32 (3D SpMV), refreshed lazily after assembly
+  bool sellF_dirty = true;
+  DevBuf<double> d_xpad;          // padded (4 doubles per node) copy of the SpMV input
+  DevBuf<int> d_blk_Fs, d_blk_S;  // CSR-stream row blocks (kernels_stream.cu)
+  int n_blk_Fs = 0, n_blk_S = 0;
   DevBuf<double> d_massdiag, d_masslump;
   DevBuf<double> d_D, d_Dinv, d_negDinv; // per velocity DoF (node-interleaved)
   DevIlu iluF, iluS;
@@ -239,6 +259,24 @@ void spgemm_schur(Handle &H); // S = B diag(negDinv) Bt on the static pattern
 void extract_diag(Handle &H);  // d_D / d_Dinv / d_negDinv per preconditioner type
 void mass_rows(Handle &H);     // d_massdiag / d_masslump from d_M
 void flush_l2(Handle &H);
+
+// ---------------------------------------------------------------- kernels_stream.cu
+void stream_build_spmv(Handle &H);
+void stream_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
+void stream_spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p);
+void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
+                      const std::vector<int> &diagpos, const std::vector<int> &colour_ptr);
+void stream_split_factors(Handle &H, DevIlu &ilu);
+void stream_trsv(Handle &H, DevIlu &ilu, double *y, cudaStream_t s);
+
+// ---------------------------------------------------------------- kernels_sell.cu
+void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
+                const std::vector<int> &ranges, int window, DevSell &out);
+void sell_fill(Handle &H, DevSell &S, const double *src);
+void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
+void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
+void sell_perm_in(Handle &H, DevIlu &ilu, const double *x, double *xp);
+void sell_perm_out(Handle &H, DevIlu &ilu, const double *yp, double *y);
 
 // ---------------------------------------------------------------- solver.cu
 void solver_alloc(Handle &H);
