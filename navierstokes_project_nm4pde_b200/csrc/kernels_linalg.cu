@@ -848,7 +848,8 @@ __global__ void __launch_bounds__(128) k_spgemm_schur(int n_rows, const int *__r
   __syncwarp();
   for (int e = b_rowptr[w]; e < b_rowptr[w + 1]; ++e) {
     const int node = b_colind[e];
-    if (node >= n_nodes_owned) continue; // ghost rows of Bt are handled by the halo variant
+    // Bt rows of ghost nodes are assembled redundantly (2-layer cell halo) and V = -1/D of ghost
+    // nodes arrives by halo exchange, so ghost nodes need no special case here
     double m[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) m[d] = b_val[int64_t(e) * DIM + d] * V[int64_t(DIM) * node + d];
@@ -867,7 +868,7 @@ __global__ void __launch_bounds__(128) k_spgemm_schur(int n_rows, const int *__r
     }
     __syncwarp();
   }
-  (void)goff_u;
+  (void)goff_u; (void)n_nodes_owned;
 }
 
 void spgemm_schur(Handle &H)

@@ -329,6 +329,7 @@ static void inner_cg_S(Handle &H, double *x, int goff_x, const double *b, double
 void precond_init(Handle &H)
 {
   extract_diag(H);
+  if (H.nranks > 1) halo_exchange_u(H, H.d_negDinv.p, 0); // -1/D of ghost nodes for the Schur product
   spgemm_schur(H);
   ilu_factor(H, H.iluF, H.Fs.val.p);
   ilu_factor(H, H.iluS, H.S.val.p);

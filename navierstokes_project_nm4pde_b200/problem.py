@@ -192,12 +192,12 @@ class NavierStokes:
 
     def neumann_rhs(self, time):
         if self._neu is None:
-            return np.zeros(self.n_u)
+            return np.zeros(self.dofs.n_u)
         nodes, shapes, xq = self._neu
         nf, nq = xq.shape[0], xq.shape[1]
         h = function_h(xq.reshape(-1, 3), time).reshape(nf, nq, 3)
         contrib = np.einsum("fnq,fqc->fnc", shapes, h)  # [face, node, comp]
-        out = np.zeros((self.n_u // 3, 3))
+        out = np.zeros((self.dofs.n_u // 3, 3))
         np.add.at(out, nodes.ravel(), contrib.reshape(-1, 3))
         return out.ravel()
 
