@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"
 
 import numpy as np  # noqa: E402
 

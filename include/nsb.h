@@ -186,7 +186,8 @@ int nsb_get_schur_values(nsb_handle h, double *vals);
 double nsb_stat(nsb_handle h, const char *name);
 /* Times `iters` launches of one kernel with CUDA events on the launching stream; returns the
  * average ms per launch and the algorithmic bytes one launch moves ("kernels").
- * which: "spmv_system", "spmv_F", "spmv_S", "assemble_step", "ilu_F", "ilu_S", "dot", "axpy" */
+ * which: "spmv_system", "spmv_F", "spmv_S", "assemble_step", "ilu_F", "ilu_S", "dot", "axpy",
+ * "add_and_dot" */
 int nsb_bench_kernel(nsb_handle h, const char *which, int iters, int flush_l2, double *ms_per_launch,
                      double *bytes_per_launch);
 /* CUDA-event stopwatch on the handle's launching stream: start (which = 0) / stop (which = 1);

@@ -1,0 +1,512 @@
+// NavierStokes.cpp -- the reference's `NavierStokes` class over the C ABI (see NavierStokes.hpp).
+// Citations are relative to /root/reference/Navier-Stokes.
+#include "NavierStokes.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kEsA = kPi / 4.0, kEsB = kPi / 2.0, kEsNu = 1e-2; // Convergence3D.hpp:54-56
+
+// QGaussSimplex<dim>(3) as forwarded to Witherden-Vincent by deal.II >= 9.4 (7 / 14 points), and
+// QGauss<1>(3); same tables as navierstokes_project_nm4pde_b200/quadrature.py.
+struct Rule {
+  std::vector<double> xi, w;
+  int dim;
+  int size() const { return int(w.size()); }
+};
+
+Rule gauss_simplex(int dim)
+{
+  Rule r;
+  r.dim = dim;
+  auto add = [&](std::initializer_list<double> p, double w) {
+    for (double v : p) r.xi.push_back(v);
+    r.w.push_back(w);
+  };
+  if (dim == 1) {
+    const double g = std::sqrt(0.6);
+    add({0.5 - 0.5 * g}, 5.0 / 18.0); add({0.5}, 8.0 / 18.0); add({0.5 + 0.5 * g}, 5.0 / 18.0);
+  } else if (dim == 2) {
+    const double s = std::sqrt(15.0);
+    add({1.0 / 3.0, 1.0 / 3.0}, 0.1125);
+    for (int k = 0; k < 2; ++k) {
+      const double a = (k == 0 ? 6.0 - s : 6.0 + s) / 21.0, w = (k == 0 ? 155.0 - s : 155.0 + s) / 2400.0;
+      add({a, a}, w); add({1.0 - 2.0 * a, a}, w); add({a, 1.0 - 2.0 * a}, w);
+    }
+  } else {
+    const double A[2] = {0.31088591926330060980, 0.092735250310891226402};
+    const double W[2] = {0.11268792571801585080 / 6.0, 0.073493043116361949544 / 6.0};
+    for (int k = 0; k < 2; ++k) {
+      const double a = A[k], b = 1.0 - 3.0 * a;
+      add({a, a, a}, W[k]); add({b, a, a}, W[k]); add({a, b, a}, W[k]); add({a, a, b}, W[k]);
+    }
+    const double c = 0.045503704125649649492, d = 0.5 - c, w = 0.042546020777081466438 / 6.0;
+    add({c, c, d}, w); add({c, d, c}, w); add({d, c, c}, w); add({c, d, d}, w); add({d, c, d}, w); add({d, d, c}, w);
+  }
+  return r;
+}
+
+const int kEdges[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+
+// P2 / P1 shape values and physical gradients at barycentric point `lam` of a simplex whose
+// barycentric gradients are gl[v][d].
+void shape_p2(int dim, const double *lam, const double gl[4][3], double *phi, double (*dphi)[3])
+{
+  const int nv = dim + 1, ne = dim == 2 ? 3 : 6;
+  for (int v = 0; v < nv; ++v) {
+    phi[v] = lam[v] * (2.0 * lam[v] - 1.0);
+    for (int d = 0; d < dim; ++d) dphi[v][d] = (4.0 * lam[v] - 1.0) * gl[v][d];
+  }
+  for (int e = 0; e < ne; ++e) {
+    const int a = kEdges[e][0], b = kEdges[e][1];
+    phi[nv + e] = 4.0 * lam[a] * lam[b];
+    for (int d = 0; d < dim; ++d) dphi[nv + e][d] = 4.0 * (lam[a] * gl[b][d] + lam[b] * gl[a][d]);
+  }
+}
+
+// barycentric gradients and |det J| of the affine simplex X[v][d]
+double bary_gradients(int dim, const double *X, double gl[4][3])
+{
+  double J[3][3] = {{0}}, Ji[3][3] = {{0}};
+  for (int r = 0; r < dim; ++r)
+    for (int k = 0; k < dim; ++k) J[r][k] = X[(k + 1) * dim + r] - X[r];
+  double det;
+  if (dim == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                 c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    Ji[0][0] = c00 / det; Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    Ji[1][0] = c01 / det; Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+    Ji[2][0] = c02 / det; Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  }
+  for (int d = 0; d < dim; ++d) {
+    gl[0][d] = 0.0;
+    for (int k = 0; k < dim; ++k) { gl[k + 1][d] = Ji[k][d]; gl[0][d] -= Ji[k][d]; }
+  }
+  return std::fabs(det);
+}
+
+// InletVelocity::vector_value (NavierStokes2D.hpp:26-44, NavierStokes3D.hpp:25-43)
+double inlet_ux(int dim, const double *x, double t, int test_case)
+{
+  const double H = 0.41;
+  if (dim == 2) {
+    const double um = 1.5, y = x[1];
+    if (test_case == 2) return 4.0 * um * y * (H - y) * std::sin(kPi * t / 8.0) / (H * H);
+    if (test_case != 1) return 4.0 * um * y * (H - y) / (H * H);
+    return 0.0;
+  }
+  const double um = 9.0, y = x[1], z = x[2];
+  if (test_case == 3) return 16.0 * um * y * z * (H - z) * (H - y) * std::sin(kPi * t / 8.0) / (H * H * H * H);
+  if (test_case != 1) return 16.0 * um * y * z * (H - z) * (H - y) / (H * H * H * H);
+  return 0.0;
+}
+
+} // namespace
+
+// InletVelocity::getMeanVelocity (NavierStokes2D.hpp:64-75, NavierStokes3D.hpp:64-75); the 2D class
+// swaps cases 2 / 3 between profile and mean -- reproduced.
+double inlet_mean_velocity(int dim, int test_case, double t)
+{
+  if (test_case == 1) return 0.0;
+  if (dim == 2) return test_case == 3 ? 2.0 * 1.5 * std::sin(t * kPi / 8.0) / 3.0 : 2.0 * 1.5 / 3.0;
+  return test_case == 3 ? 4.0 * 9.0 * std::sin(t * kPi / 8.0) / 9.0 : 4.0 * 9.0 / 9.0;
+}
+
+// ExactSolution::vector_value / gradient_tensor (Convergence3D.hpp:59-132)
+void ethier_steinman(const double X[3], double t, double u[3], double &p, double g[3][3])
+{
+  const double a = kEsA, b = kEsB, x = X[0], y = X[1], z = X[2];
+  const double e = -a * std::exp(-kEsNu * b * b * t);
+  const double ex = std::exp(a * x), ey = std::exp(a * y), ez = std::exp(a * z);
+  u[0] = e * (ex * std::sin(a * y + b * z) + ez * std::cos(a * x + b * y));
+  u[1] = e * (ey * std::sin(a * z + b * x) + ex * std::cos(a * y + b * z));
+  u[2] = e * (ez * std::sin(a * x + b * y) + ey * std::cos(a * z + b * x));
+  const double f = -(a * a * std::exp(-2 * kEsNu * b * b * t)) / 2.0;
+  p = f * (2.0 * std::sin(a * x + b * y) * std::cos(a * z + b * x) * std::exp(a * (y + z)) +
+           2.0 * std::sin(a * y + b * z) * std::cos(a * x + b * y) * std::exp(a * (x + z)) +
+           2.0 * std::sin(a * z + b * x) * std::cos(a * y + b * z) * std::exp(a * (x + y)) + std::exp(2 * a * x) +
+           std::exp(2 * a * y) + std::exp(2 * a * z));
+  g[0][0] = e * (a * ex * std::sin(a * y + b * z) - a * ez * std::sin(a * x + b * y));
+  g[0][1] = e * (a * ex * std::cos(a * y + b * z) - b * ez * std::sin(a * x + b * y));
+  g[0][2] = e * (b * ex * std::cos(a * y + b * z) + a * ez * std::cos(a * x + b * y));
+  g[1][0] = e * (b * ey * std::cos(a * z + b * x) + a * ex * std::cos(a * y + b * z));
+  g[1][1] = e * (a * ey * std::sin(a * z + b * x) - a * ex * std::sin(a * y + b * z));
+  g[1][2] = e * (a * ey * std::cos(a * z + b * x) - b * ex * std::sin(a * y + b * z));
+  g[2][0] = e * (a * ez * std::cos(a * x + b * y) - b * ey * std::sin(a * z + b * x));
+  g[2][1] = e * (b * ez * std::cos(a * x + b * y) + a * ey * std::cos(a * z + b * x));
+  g[2][2] = e * (a * ez * std::sin(a * x + b * y) - a * ey * std::sin(a * z + b * x));
+}
+
+NavierStokes::NavierStokes(Variant variant_, const std::string &mesh_file_name_, unsigned degree_velocity,
+                           unsigned degree_pressure, double T_, double deltat_, int test_case_)
+  : variant(variant_), dim(variant_ == Variant::Cylinder2D ? 2 : 3), mesh_file_name(mesh_file_name_), T(T_),
+    deltat(deltat_), test_case(test_case_), nu(variant_ == Variant::Convergence3D ? 1e-2 : 1e-3)
+{
+  if (degree_velocity != 2 || degree_pressure != 1)
+    throw std::invalid_argument("NavierStokes: only Taylor-Hood P2-P1 is on the device path");
+}
+
+NavierStokes::~NavierStokes()
+{
+  if (engine) nsb_destroy(engine);
+  if (dofs) nsh_dofs_free(dofs);
+  if (mesh) nsh_mesh_free(mesh);
+}
+
+void NavierStokes::check(int rc, const char *what) const
+{
+  if (rc >= 0) return;
+  const char *msg = nsb_last_error(engine);
+  throw std::runtime_error(std::string(what) + ": " + (msg ? msg : "error") + " (code " + std::to_string(rc) + ")");
+}
+
+// NavierStokes::setup (NavierStokes2D.cpp:2-157)
+void NavierStokes::setup()
+{
+  if (verbose) std::cout << "Initializing the mesh" << std::endl;
+  if (mesh_file_name.rfind("gen:", 0) == 0) {
+    std::vector<std::string> tok;
+    std::stringstream ss(mesh_file_name);
+    for (std::string t; std::getline(ss, t, ':');) tok.push_back(t);
+    auto num = [&](size_t i, int def) { return tok.size() > i ? std::atoi(tok[i].c_str()) : def; };
+    if (tok.size() > 1 && tok[1] == "cylinder2d") mesh = nsh_mesh_cylinder2d(num(2, 1));
+    else if (tok.size() > 1 && tok[1] == "cylinder3d") mesh = nsh_mesh_cylinder3d(num(2, 1), num(3, 3));
+    else if (tok.size() > 1 && tok[1] == "cube") mesh = nsh_mesh_cube(num(2, 4));
+  } else
+    mesh = nsh_mesh_read_msh(mesh_file_name.c_str());
+  if (!mesh) throw std::runtime_error("cannot read mesh " + mesh_file_name);
+  if (nsh_mesh_dim(mesh) != dim) throw std::runtime_error("mesh dimension does not match the problem class");
+  if (verbose) std::cout << "  Number of elements = " << nsh_mesh_n_cells(mesh) << std::endl;
+  dofs = nsh_dofs_create(mesh);
+  n_nodes = nsh_dofs_n_nodes(dofs);
+  n_u = dim * n_nodes;
+  n_p = nsh_dofs_n_p(dofs);
+  N = n_u + n_p;
+  dpc = nsh_dofs_per_cell(dofs);
+  if (verbose) std::cout << "  Number of DoFs = " << N << " (" << n_u << " + " << n_p << ")" << std::endl;
+
+  // Dirichlet nodes (interpolate_boundary_values, NavierStokes2D.cpp:328-353; Convergence3D.cpp:364-368)
+  auto boundary_nodes = [&](std::initializer_list<int32_t> ids) {
+    std::vector<int32_t> idv(ids), out(size_t(nsh_dofs_boundary_nodes(dofs, mesh, idv.data(), int32_t(idv.size()), nullptr)));
+    nsh_dofs_boundary_nodes(dofs, mesh, idv.data(), int32_t(idv.size()), out.data());
+    return out;
+  };
+  if (variant == Variant::Convergence3D) {
+    dir_nodes = boundary_nodes({0, 1, 2, 4, 5});
+    dir_is_inlet.assign(dir_nodes.size(), 0);
+  } else {
+    const std::vector<int32_t> inlet = boundary_nodes({0}), walls = boundary_nodes({2, 3});
+    std::vector<char> on_inlet(size_t(n_nodes), 0), on_wall(size_t(n_nodes), 0);
+    for (int32_t v : inlet) on_inlet[v] = 1;
+    for (int32_t v : walls) on_wall[v] = 1;
+    dir_nodes = inlet;
+    for (int32_t v : walls)
+      if (!on_inlet[v]) dir_nodes.push_back(v);
+    for (int32_t v : dir_nodes) dir_is_inlet.push_back(on_inlet[v] && !on_wall[v]); // the second call overwrites with zero
+  }
+  for (int32_t v : dir_nodes)
+    for (int c = 0; c < dim; ++c) dir_rows.push_back(dim * v + c);
+  const int32_t nf = nsh_dofs_boundary_faces(dofs, mesh, 3, nullptr, nullptr);
+  obstacle_cells.resize(size_t(nf));
+  obstacle_faces.resize(size_t(nf));
+  if (nf) nsh_dofs_boundary_faces(dofs, mesh, 3, obstacle_cells.data(), obstacle_faces.data());
+
+  int rc = nsb_create(&engine, dim, device, 1, 0, nullptr);
+  if (rc < 0) throw std::runtime_error(std::string("nsb_create: ") + nsb_last_error(nullptr));
+  nsb_params prm;
+  check(nsb_default_params(&prm, int(variant)), "nsb_default_params");
+  prm.nu = nu;
+  prm.deltat = deltat;
+  prm.ilu_ordering = ilu_ordering;
+  check(nsb_set_params(engine, &prm), "nsb_set_params");
+  check(nsb_set_mesh(engine, nsh_mesh_n_cells(mesh), nsh_dofs_cell_coords(dofs), nsh_dofs_cell_dofs(dofs), n_u, n_p, n_u,
+                     n_p),
+        "nsb_set_mesh");
+  const Rule q = gauss_simplex(dim); // QGaussSimplex<dim>(fe->degree + 1), NavierStokes2D.cpp:45
+  check(nsb_set_quadrature(engine, q.size(), q.xi.data(), q.w.data()), "nsb_set_quadrature");
+  check(nsb_finalize_setup(engine), "nsb_finalize_setup");
+  check(nsb_set_dirichlet(engine, int32_t(dir_rows.size()), dir_rows.data()), "nsb_set_dirichlet");
+  solution.assign(size_t(N), 0.0);
+}
+
+void NavierStokes::dirichlet_values(double time, std::vector<double> &vals) const
+{
+  const double *xyz = nsh_dofs_node_xyz(dofs);
+  vals.assign(dir_rows.size(), 0.0);
+  for (size_t k = 0; k < dir_nodes.size(); ++k) {
+    const double *x = xyz + size_t(dim) * dir_nodes[k];
+    if (variant == Variant::Convergence3D) {
+      double u[3], p, g[3][3];
+      ethier_steinman(x, time, u, p, g);
+      for (int c = 0; c < 3; ++c) vals[3 * k + c] = u[c];
+    } else if (dir_is_inlet[k])
+      vals[size_t(dim) * k] = inlet_ux(dim, x, time, test_case);
+  }
+}
+
+// Neumann face term of Convergence3D.cpp:309-330: sum_q h(x_q) . phi_i JxW on faces with id 3,
+// h = nu du/dn - p n with n = +e_y (FunctionH, Convergence3D.hpp:159-175)
+void NavierStokes::neumann_rhs(double time, std::vector<double> &rhs) const
+{
+  rhs.assign(size_t(n_u), 0.0);
+  const Rule q = gauss_simplex(2);
+  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
+  const double *cc = nsh_dofs_cell_coords(dofs);
+  for (size_t f = 0; f < obstacle_cells.size(); ++f) {
+    const int c = obstacle_cells[f], lf = obstacle_faces[f];
+    int vs[3], nv = 0;
+    for (int v = 0; v < 4; ++v)
+      if (v != lf) vs[nv++] = v;
+    const double *X = cc + size_t(c) * 12;
+    double e1[3], e2[3];
+    for (int d = 0; d < 3; ++d) { e1[d] = X[vs[1] * 3 + d] - X[vs[0] * 3 + d]; e2[d] = X[vs[2] * 3 + d] - X[vs[0] * 3 + d]; }
+    const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double area2 = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+    for (int iq = 0; iq < q.size(); ++iq) {
+      double lam[4] = {0, 0, 0, 0};
+      lam[vs[0]] = 1.0 - q.xi[2 * iq] - q.xi[2 * iq + 1];
+      lam[vs[1]] = q.xi[2 * iq];
+      lam[vs[2]] = q.xi[2 * iq + 1];
+      double xq[3] = {0, 0, 0};
+      for (int v = 0; v < 4; ++v)
+        for (int d = 0; d < 3; ++d) xq[d] += lam[v] * X[v * 3 + d];
+      double u[3], p, g[3][3];
+      ethier_steinman(xq, time, u, p, g);
+      double h[3] = {kEsNu * g[0][1], kEsNu * g[1][1] - p, kEsNu * g[2][1]};
+      const double jxw = q.w[iq] * area2;
+      // P2 shape values (only nodes on the face are non-zero there)
+      for (int v = 0; v < 4; ++v) {
+        const double ph = lam[v] * (2.0 * lam[v] - 1.0);
+        if (ph == 0.0) continue;
+        const int node = cd[size_t(c) * dpc + v * 4] / 3;
+        for (int d = 0; d < 3; ++d) rhs[size_t(3) * node + d] += h[d] * ph * jxw;
+      }
+      for (int e = 0; e < 6; ++e) {
+        const double ph = 4.0 * lam[kEdges[e][0]] * lam[kEdges[e][1]];
+        if (ph == 0.0) continue;
+        const int node = cd[size_t(c) * dpc + 16 + e * 3] / 3;
+        for (int d = 0; d < 3; ++d) rhs[size_t(3) * node + d] += h[d] * ph * jxw;
+      }
+    }
+  }
+}
+
+void NavierStokes::initial_condition(std::vector<double> &x) const
+{
+  x.assign(size_t(N), 0.0); // FunctionU0 = 0 for the cylinders (NavierStokes2D.hpp:140-150)
+  if (variant != Variant::Convergence3D) return;
+  const double *nx = nsh_dofs_node_xyz(dofs), *px = nsh_dofs_p_xyz(dofs);
+  double u[3], p, g[3][3];
+  for (int n = 0; n < n_nodes; ++n) {
+    ethier_steinman(nx + size_t(3) * n, 0.0, u, p, g);
+    for (int c = 0; c < 3; ++c) x[size_t(3) * n + c] = u[c];
+  }
+  for (int v = 0; v < n_p; ++v) {
+    ethier_steinman(px + size_t(3) * v, 0.0, u, p, g);
+    x[size_t(n_u) + v] = p;
+  }
+}
+
+void NavierStokes::assemble(const double &time)
+{
+  if (verbose) std::cout << "===============================================\nAssembling the system" << std::endl;
+  std::vector<double> vals;
+  dirichlet_values(time, vals);
+  check(nsb_set_dirichlet_values(engine, vals.data()), "nsb_set_dirichlet_values");
+  check(nsb_assemble_first(engine, time), "nsb_assemble_first");
+}
+
+void NavierStokes::assemble_time_step(const double &time)
+{
+  std::vector<double> vals;
+  dirichlet_values(time, vals);
+  check(nsb_set_dirichlet_values(engine, vals.data()), "nsb_set_dirichlet_values");
+  check(nsb_assemble_step(engine, time), "nsb_assemble_step");
+}
+
+void NavierStokes::solve_time_step(double)
+{
+  int32_t its = 0;
+  double tp = 0, ts = 0;
+  check(nsb_solve_step(engine, &its, &tp, &ts), "nsb_solve_step");
+  time_prec.push_back(tp);
+  time_solve.push_back(ts);
+  gmres_iterations.push_back(its);
+  if (verbose) {
+    std::cout << "Time taken to initialize preconditioner: " << tp << " seconds" << std::endl;
+    std::cout << "Time taken to solve Navier Stokes problem: " << ts << " seconds" << std::endl;
+    std::cout << "Result:  " << its << " GMRES iterations" << std::endl;
+  }
+  check(nsb_get_solution(engine, solution.data()), "nsb_get_solution"); // solution = solution_owned (:637)
+}
+
+// NavierStokes2D.cpp:752-859 (QGauss<1>(3) on the cylinder edges, force = (nu grad u - p I) n) and
+// NavierStokes3D.cpp:744-840 (QGaussSimplex<2>(3), tangential formula).
+std::vector<double> NavierStokes::compute_forces()
+{
+  const Rule q = gauss_simplex(dim - 1);
+  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
+  const double *cc = nsh_dofs_cell_coords(dofs);
+  const int nv = dim + 1, n2 = dim == 2 ? 6 : 10;
+  double drag = 0.0, lift = 0.0;
+  for (size_t f = 0; f < obstacle_cells.size(); ++f) {
+    const int c = obstacle_cells[f], lf = obstacle_faces[f];
+    const double *X = cc + size_t(c) * nv * dim;
+    double gl[4][3];
+    bary_gradients(dim, X, gl);
+    // outward unit normal of the face opposite to vertex lf: -grad(lambda_lf) normalised
+    double nrm = 0.0, n_out[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) nrm += gl[lf][d] * gl[lf][d];
+    nrm = std::sqrt(nrm);
+    for (int d = 0; d < dim; ++d) n_out[d] = -gl[lf][d] / nrm;
+    int vs[3], k = 0;
+    for (int v = 0; v < nv; ++v)
+      if (v != lf) vs[k++] = v;
+    double meas; // |edge| in 2D, 2 * area in 3D (weights of the reference face sum to 1 resp. 1/2)
+    if (dim == 2) {
+      meas = std::hypot(X[vs[1] * 2] - X[vs[0] * 2], X[vs[1] * 2 + 1] - X[vs[0] * 2 + 1]);
+    } else {
+      double e1[3], e2[3];
+      for (int d = 0; d < 3; ++d) { e1[d] = X[vs[1] * 3 + d] - X[vs[0] * 3 + d]; e2[d] = X[vs[2] * 3 + d] - X[vs[0] * 3 + d]; }
+      const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+      meas = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+    }
+    // nodal values of this cell (FESystem order: per vertex [u.., p], then per edge [u..])
+    double U[10][3], P[4];
+    for (int v = 0; v < nv; ++v) {
+      for (int d = 0; d < dim; ++d) U[v][d] = solution[cd[size_t(c) * dpc + v * (dim + 1) + d]];
+      P[v] = solution[cd[size_t(c) * dpc + v * (dim + 1) + dim]];
+    }
+    for (int e = 0; e < n2 - nv; ++e)
+      for (int d = 0; d < dim; ++d) U[nv + e][d] = solution[cd[size_t(c) * dpc + nv * (dim + 1) + e * dim + d]];
+    for (int iq = 0; iq < q.size(); ++iq) {
+      double lam[4] = {0, 0, 0, 0};
+      if (dim == 2) { lam[vs[0]] = 1.0 - q.xi[iq]; lam[vs[1]] = q.xi[iq]; }
+      else { lam[vs[0]] = 1.0 - q.xi[2 * iq] - q.xi[2 * iq + 1]; lam[vs[1]] = q.xi[2 * iq]; lam[vs[2]] = q.xi[2 * iq + 1]; }
+      double phi[10], dphi[10][3];
+      shape_p2(dim, lam, gl, phi, dphi);
+      double G[3][3] = {{0}}, p = 0.0; // G[i][j] = d u_i / d x_j
+      for (int a = 0; a < n2; ++a)
+        for (int i = 0; i < dim; ++i)
+          for (int j = 0; j < dim; ++j) G[i][j] += U[a][i] * dphi[a][j];
+      for (int v = 0; v < nv; ++v) p += P[v] * lam[v];
+      const double jxw = q.w[iq] * meas;
+      double n[3] = {-n_out[0], -n_out[1], -n_out[2]}; // normal_vector = -fe_face_values.normal_vector(q)
+      if (dim == 2) {
+        double force[2];
+        for (int i = 0; i < 2; ++i) force[i] = (nu * (G[i][0] * n[0] + G[i][1] * n[1]) - p * n[i]) * jxw;
+        drag += force[0];
+        lift += force[1];
+      } else {
+        const double nx = n[0], ny = n[1];
+        const double t[3] = {ny, -nx, 0.0}, t2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        double ngt = 0.0; // n * grad u * (t / |t|^2)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) ngt += n[i] * G[i][j] * t[j] / t2;
+        drag += (rho * nu * ngt * ny - p * nx) * jxw;
+        lift -= (rho * nu * ngt * nx + p * ny) * jxw;
+      }
+    }
+  }
+  const double mean_v = inlet_mean_velocity(dim, test_case, time_now), D = 0.1, H = 0.41;
+  const double den = dim == 2 ? mean_v * mean_v * D : rho * mean_v * mean_v * D * H;
+  const double c_d = 2.0 * drag / den, c_l = 2.0 * lift / den;
+  if (verbose) std::cout << "Coeff:\t " << c_d << " Coeff:\t " << c_l << std::endl;
+  coefficients_history.push_back({c_d, c_l});
+  return {c_d, c_l};
+}
+
+// NavierStokes::solve (NavierStokes2D.cpp:699-750, NavierStokes3D.cpp:694-742, Convergence3D.cpp:724-764)
+void NavierStokes::solve()
+{
+  if (verbose) std::cout << "===============================================\nApplying the initial condition" << std::endl;
+  initial_condition(solution);
+  check(nsb_set_solution(engine, solution.data()), "nsb_set_solution");
+  double c_D_max = -999, c_L_min = 999, time = 0;
+  unsigned time_step = 0;
+  std::vector<double> neu;
+  while (time < T - 0.5 * deltat) {
+    if (variant == Variant::Convergence3D) { // function_h.set_time(time) BEFORE the increment (Convergence3D.cpp:747-750)
+      neumann_rhs(time, neu);
+      check(nsb_set_neumann_rhs(engine, neu.data()), "nsb_set_neumann_rhs");
+    }
+    time += deltat;
+    ++time_step;
+    time_now = time;
+    if (verbose) std::cout << "n = " << std::setw(3) << time_step << ", t = " << std::setw(5) << time << ":" << std::flush;
+    if (time == deltat) assemble(time);
+    else assemble_time_step(time);
+    solve_time_step(time);
+    const bool forces = variant == Variant::Cylinder2D || (variant == Variant::Cylinder3D && time > forces_after);
+    if (forces) {
+      const std::vector<double> c = compute_forces();
+      c_D_max = std::max(c_D_max, c[0]);
+      c_L_min = std::min(c_L_min, c[1]);
+    }
+    if (max_steps > 0 && int(time_step) >= max_steps) break;
+  }
+  if (verbose && variant != Variant::Convergence3D) {
+    std::cout << "===============================================\nDrag Coefficient Max ----->   " << c_D_max << "\n\n"
+              << "Lift Coefficient Min ----->   " << c_L_min << "\n===============================================" << std::endl;
+  }
+}
+
+// Convergence3D.cpp:766-794: VectorTools::integrate_difference over the velocity components against
+// the exact solution at t = T.  The reference integrates with QGaussSimplex<3>(degree + 2); the
+// 14-point degree-5 rule is used here (the integrand error is far below the discretisation error).
+double NavierStokes::compute_error(const VectorTools::NormType &norm_type)
+{
+  const Rule q = gauss_simplex(3);
+  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
+  const double *cc = nsh_dofs_cell_coords(dofs);
+  const int nc = nsh_mesh_n_cells(mesh);
+  double e2 = 0.0, h2 = 0.0;
+  for (int c = 0; c < nc; ++c) {
+    const double *X = cc + size_t(c) * 12;
+    double gl[4][3];
+    const double det = bary_gradients(3, X, gl);
+    double U[10][3];
+    for (int v = 0; v < 4; ++v)
+      for (int d = 0; d < 3; ++d) U[v][d] = solution[cd[size_t(c) * dpc + v * 4 + d]];
+    for (int e = 0; e < 6; ++e)
+      for (int d = 0; d < 3; ++d) U[4 + e][d] = solution[cd[size_t(c) * dpc + 16 + e * 3 + d]];
+    for (int iq = 0; iq < q.size(); ++iq) {
+      const double lam[4] = {1.0 - q.xi[3 * iq] - q.xi[3 * iq + 1] - q.xi[3 * iq + 2], q.xi[3 * iq], q.xi[3 * iq + 1],
+                             q.xi[3 * iq + 2]};
+      double xq[3] = {0, 0, 0};
+      for (int v = 0; v < 4; ++v)
+        for (int d = 0; d < 3; ++d) xq[d] += lam[v] * X[v * 3 + d];
+      double phi[10], dphi[10][3], uh[3] = {0, 0, 0}, gh[3][3] = {{0}};
+      shape_p2(3, lam, gl, phi, dphi);
+      for (int a = 0; a < 10; ++a)
+        for (int i = 0; i < 3; ++i) {
+          uh[i] += U[a][i] * phi[a];
+          for (int j = 0; j < 3; ++j) gh[i][j] += U[a][i] * dphi[a][j];
+        }
+      double ue[3], pe, ge[3][3];
+      ethier_steinman(xq, T, ue, pe, ge);
+      const double jxw = q.w[iq] * det;
+      for (int i = 0; i < 3; ++i) {
+        e2 += jxw * (uh[i] - ue[i]) * (uh[i] - ue[i]);
+        for (int j = 0; j < 3; ++j) h2 += jxw * (gh[i][j] - ge[i][j]) * (gh[i][j] - ge[i][j]);
+      }
+    }
+  }
+  return norm_type == VectorTools::L2_norm ? std::sqrt(e2) : std::sqrt(e2 + h2);
+}

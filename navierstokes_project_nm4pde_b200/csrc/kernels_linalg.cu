@@ -315,7 +315,7 @@ void vec_pointwise_out(Handle &H, int n, const double *d, const double *x, doubl
 
 // Deterministic two-stage reduction: fixed grid, fixed per-block order, the last block to finish
 // (ticket) adds the block partials in index order.  scratch layout: [0..1023] partials, then ticket.
-constexpr int kRedBlocks = 592; // 148 * 4
+constexpr int kRedBlocks = 888; // 148 * 6 (<= 1024 partial slots)
 __device__ __forceinline__ double block_sum(double v)
 {
   __shared__ double sh[8];
@@ -353,12 +353,22 @@ __device__ __forceinline__ void finish_reduce(double part, double *partials, uns
   }
 }
 
+// Both reductions keep 4 independent element groups in flight per thread (the loads of one group
+// do not depend on the previous one), which is what a bandwidth-bound 16-24 B/element stream needs
+// to cover the HBM latency at full occupancy; the summation order is fixed by (grid, block) only.
 __global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ x, const double *__restrict__ y,
                                              double *partials, unsigned *ticket, double *out)
 {
-  double v = 0.0;
-  GRID_STRIDE(i, n) v += x[i] * y[i];
-  const double s = block_sum(v);
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double a0 = x[i], a1 = x[i + stride], a2 = x[i + 2 * stride], a3 = x[i + 3 * stride];
+    const double b0 = y[i], b1 = y[i + stride], b2 = y[i + 2 * stride], b3 = y[i + 3 * stride];
+    v0 += a0 * b0; v1 += a1 * b1; v2 += a2 * b2; v3 += a3 * b3;
+  }
+  for (; i < n; i += stride) v0 += x[i] * y[i];
+  const double s = block_sum((v0 + v1) + (v2 + v3));
   finish_reduce(s, partials, ticket, out);
 }
 
@@ -368,14 +378,26 @@ __global__ void __launch_bounds__(256) k_add_and_dot(int n, double *vv, const do
                                                      unsigned *ticket, double *out)
 {
   const double aa = sign * (*a);
-  double v = 0.0;
-  GRID_STRIDE(i, n) {
-    const double t = vv[i] + aa * vp[i];
-    const double o = (vn == vv) ? t : vn[i];
-    vv[i] = t;
-    v += t * o;
+  const bool self = (vn == vv);
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double w0 = vv[i], w1 = vv[i + stride], w2 = vv[i + 2 * stride], w3 = vv[i + 3 * stride];
+    const double p0 = vp[i], p1 = vp[i + stride], p2 = vp[i + 2 * stride], p3 = vp[i + 3 * stride];
+    const double t0 = w0 + aa * p0, t1 = w1 + aa * p1, t2 = w2 + aa * p2, t3 = w3 + aa * p3;
+    double o0 = t0, o1 = t1, o2 = t2, o3 = t3;
+    if (!self) { o0 = vn[i]; o1 = vn[i + stride]; o2 = vn[i + 2 * stride]; o3 = vn[i + 3 * stride]; }
+    vv[i] = t0; vv[i + stride] = t1; vv[i + 2 * stride] = t2; vv[i + 3 * stride] = t3;
+    v0 += t0 * o0; v1 += t1 * o1; v2 += t2 * o2; v3 += t3 * o3;
   }
-  const double s = block_sum(v);
+  for (; i < n; i += stride) {
+    const double t = vv[i] + aa * vp[i];
+    const double o = self ? t : vn[i];
+    vv[i] = t;
+    v0 += t * o;
+  }
+  const double s = block_sum((v0 + v1) + (v2 + v3));
   finish_reduce(s, partials, ticket, out);
 }
 
@@ -791,6 +813,7 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
   const int nvals = ilu.n * ilu.bs_rhs;
   cudaStream_t s = H.stream;
   if (!ilu.graph_f) {
+    if (ilu.sell) ilu.io.alloc(2);
     NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * size_t(ilu.sell ? 4 * ilu.n : nvals)));
     cudaGraph_t g;
     const int64_t before = H.launches;
@@ -805,11 +828,10 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;
   }
-  if (ilu.sell) {
-    sell_perm_in(H, ilu, x, ilu.graph_x);
+  if (ilu.sell) { // permutation in / out fused into the first forward and every backward launch
+    sell_set_io(H, ilu, x, y);
     NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
-    sell_perm_out(H, ilu, ilu.graph_x, y);
-    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1) - 1;
+    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1);
     return;
   }
   const unsigned pg = vgrid(nvals);

@@ -30,19 +30,28 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
   asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-// MODE 0: y[3r+d]  = sum            (SpMV, unpadded output)
-// MODE 1: y[4r+d] -= sum            (forward substitution of one colour; y is the padded staging)
-// MODE 2: y[4r+d]  = y*dinv - sum   (backward substitution of one colour)
+// in / out vectors of a captured triangular solve: the graph bakes kernel arguments, so the
+// caller's pointers are passed through this device-resident slot (set by k_set_io before launch)
+struct TrsvIo { const double *x; double *y; };
+__global__ void k_set_io(TrsvIo *io, const double *x, double *y) { io->x = x; io->y = y; }
+
+// MODE 0: y[3r+d]  = sum                          (SpMV, unpadded output)
+// MODE 1: y[4r+d]  = x[3 order[r]+d] - sum        (forward substitution of one colour; y is the padded
+//                                                  staging in factor order, x the caller's vector:
+//                                                  the permutation is fused into the sweep)
+// MODE 2: y[4r+d]  = y*dinv - sum, also stored to out[3 order[r]+d]   (backward substitution)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__restrict__ slice_ptr,
                                                const int *__restrict__ rowid, const int *__restrict__ col,
                                                const double *__restrict__ val, const double *xp, double *y,
-                                               const double *__restrict__ dinv)
+                                               const double *__restrict__ dinv, const int *__restrict__ order = nullptr,
+                                               const TrsvIo *__restrict__ io = nullptr)
 {
+  // one warp per slice, no grid-stride loop: slices are length-sorted inside windows, so a fixed
+  // stride would hand the same warps the long slices of every window (ncu: 52% achieved occupancy)
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int s = s0 + warp; s < s1; s += nwarps) {
+  const int s = s0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (s < s1) {
     const int base = slice_ptr[s];
     const int len = (slice_ptr[s + 1] - base) >> 5;
     const int r = rowid[(int64_t(s) << 5) + lane];
@@ -84,8 +93,16 @@ __global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__rest
         o[0] = a0; o[1] = a1; o[2] = a2;
       } else {
         double *o = y + 4 * int64_t(r);
-        if (MODE == 1) { o[0] -= a0; o[1] -= a1; o[2] -= a2; }
-        else { const double di = dinv[r]; o[0] = o[0] * di - a0; o[1] = o[1] * di - a1; o[2] = o[2] * di - a2; }
+        if (MODE == 1) {
+          const double *xi = io->x + 3 * int64_t(order[r]);
+          o[0] = xi[0] - a0; o[1] = xi[1] - a1; o[2] = xi[2] - a2; o[3] = 0.0;
+        } else {
+          const double di = dinv[r];
+          const double r0 = o[0] * di - a0, r1 = o[1] * di - a1, r2 = o[2] * di - a2;
+          o[0] = r0; o[1] = r1; o[2] = r2;
+          double *yo = io->y + 3 * int64_t(order[r]);
+          yo[0] = r0; yo[1] = r1; yo[2] = r2;
+        }
       }
     }
   }
@@ -108,24 +125,6 @@ __global__ void k_pad3(int n_nodes, int n_owned, int goff, const double *__restr
     xp[t] = d < 3 ? x[int64_t(3) * i + (i >= n_owned ? goff : 0) + d] : 0.0;
   }
 }
-// staging for the triangular solves: xp[4k+d] = x[3*order[k]+d] and back
-__global__ void k_perm_gather34(int n, const int *__restrict__ order, const double *__restrict__ x,
-                                double *__restrict__ xp)
-{
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 4; t += gridDim.x * blockDim.x) {
-    const int k = t >> 2, d = t & 3;
-    xp[t] = d < 3 ? x[int64_t(3) * order[k] + d] : 0.0;
-  }
-}
-__global__ void k_perm_scatter43(int n, const int *__restrict__ order, const double *__restrict__ yp,
-                                 double *__restrict__ y)
-{
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 3; t += gridDim.x * blockDim.x) {
-    const int k = t / 3, d = t - 3 * k;
-    y[int64_t(3) * order[k] + d] = yp[int64_t(4) * k + d];
-  }
-}
-
 // Build SELL-32 for the rows of `rowptr/colind`.  ranges: row ranges that must not share a slice
 // (colours); inside a range rows are sorted by length (descending) within windows of `window`
 // rows.  src[e]: index of CSR entry e in the value array the SELL values are filled from.
@@ -186,10 +185,7 @@ void sell_fill(Handle &H, DevSell &S, const double *src)
   H.launches++;
 }
 
-static inline unsigned sell_grid(int n_slices)
-{
-  return unsigned(std::max(1, std::min((n_slices + 7) / 8, kSM * 8)));
-}
+static inline unsigned sell_grid(int n_slices) { return unsigned(std::max(1, (n_slices + 7) / 8)); }
 
 // y_u = F_s x_u (3D).  x is copied once into the padded staging vector.
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u)
@@ -209,34 +205,32 @@ void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u)
 }
 
 // in-place triangular solves on the padded staging vector (permuted index space)
+// yp: padded staging (factor order).  The caller's in / out vectors come through ilu.io (sell_set_io).
+// Colour 0 has no lower part (zero-length slices): its forward launch is the fused permutation.
 void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
 {
   const int nc = int(ilu.colour_ptr.size()) - 1;
-  for (int c = 1; c < nc; ++c) {
+  const TrsvIo *io = reinterpret_cast<const TrsvIo *>(ilu.io.p);
+  for (int c = 0; c < nc; ++c) {
     const int a = ilu.sellL.range_slice[c], b = ilu.sellL.range_slice[c + 1];
     if (b <= a) continue;
     k_sell3<1><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellL.slice_ptr.p, ilu.sellL.rowid.p, ilu.sellL.col.p,
-                                               ilu.sellL.val.p, yp, yp, nullptr);
+                                               ilu.sellL.val.p, yp, yp, nullptr, ilu.order.p, io);
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int a = ilu.sellU.range_slice[c], b = ilu.sellU.range_slice[c + 1];
     if (b <= a) continue;
     k_sell3<2><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellU.slice_ptr.p, ilu.sellU.rowid.p, ilu.sellU.col.p,
-                                               ilu.sellU.val.p, yp, yp, ilu.dinv.p);
+                                               ilu.sellU.val.p, yp, yp, ilu.dinv.p, ilu.order.p, io);
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());
 }
 
-void sell_perm_in(Handle &H, DevIlu &ilu, const double *x, double *xp)
+void sell_set_io(Handle &H, DevIlu &ilu, const double *x, double *y)
 {
-  k_perm_gather34<<<unsigned(std::min((ilu.n * 4 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(ilu.n, ilu.order.p, x, xp);
-  H.launches++;
-}
-void sell_perm_out(Handle &H, DevIlu &ilu, const double *yp, double *y)
-{
-  k_perm_scatter43<<<unsigned(std::min((ilu.n * 3 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(ilu.n, ilu.order.p, yp, y);
+  k_set_io<<<1, 1, 0, H.stream>>>(reinterpret_cast<TrsvIo *>(ilu.io.p), x, y);
   H.launches++;
 }
 

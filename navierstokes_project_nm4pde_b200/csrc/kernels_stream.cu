@@ -14,6 +14,8 @@
 //   MODE 2: y  = y * dinv - U y     (backward substitution of one colour, Ifpack's scaled U)
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "nsb_internal.hpp"
 
 namespace nsb {
@@ -21,6 +23,13 @@ namespace nsb {
 constexpr int kCH = 1024;     // entries per block
 constexpr int kMaxRows = 128; // rows per block (phase 2 parallelism; also bounds blocks of empty rows)
 constexpr int kSM = 148;
+// rows of one colour are length-sorted only inside windows of this many rows, so that a slice
+// gathers from a narrow band of the vector (L2 locality) at <2% padding
+static int sell_window()
+{
+  const char *e = getenv("NSB_SELL_WINDOW");
+  return e ? std::max(32, atoi(e)) : 4096;
+}
 
 template <int BS, int MODE>
 __global__ void __launch_bounds__(256) k_stream(const int *__restrict__ blk, const int *__restrict__ rowptr,
@@ -227,8 +236,8 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
   ilu.stream = true;
   ilu.sell = false;
   if (ilu.bs_rhs == 3) { // SELL-32 copies of the factors for the 3-component solves
-    sell_build(Lp, Lc, mapL, colour_ptr, 1 << 30, ilu.sellL);
-    sell_build(Up, Uc, mapU, colour_ptr, 1 << 30, ilu.sellU);
+    sell_build(Lp, Lc, mapL, colour_ptr, sell_window(), ilu.sellL);
+    sell_build(Up, Uc, mapU, colour_ptr, sell_window(), ilu.sellU);
     ilu.sell = true;
   }
   (void)H;

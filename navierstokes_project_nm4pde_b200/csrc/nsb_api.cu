@@ -838,6 +838,12 @@ extern "C" int nsb_bench_kernel(nsb_handle h, const char *which, int iters, int 
     } else if (w == "axpy") {
       bytes = 24.0 * (nu + np);
       run = [&] { vec_axpy(H, H.n_owned(), 1e-30, a, b); };
+    } else if (w == "add_and_dot") {
+      // one modified Gram-Schmidt step of the inner GMRES on F: vv -= h v_prev; h' = vv . v_next
+      bytes = 32.0 * nu;
+      run = [&] {
+        vec_add_and_dot_dev(H, H.nu_owned(), b, H.ws->scal.p + 221, -1e-30, a, H.ws->tu[0].p, H.ws->scal.p + 220);
+      };
     } else
       throw ArgError("nsb_bench_kernel: unknown kernel name");
     cudaEvent_t e0, e1;

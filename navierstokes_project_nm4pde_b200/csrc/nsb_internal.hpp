@@ -117,6 +117,7 @@ struct DevIlu {
   // multicolour mode: split L / U factors and per-colour row blocks for the CSR-stream solves
   bool stream = false, sell = false;
   DevSell sellL, sellU;
+  DevBuf<double> io;              // TrsvIo slot: caller's in / out pointers of the captured solve
   DevBuf<int> Lp, Lc, Up, Uc, mapL, mapU, blkL, blkU;
   DevBuf<double> Lv, Uv;
   std::vector<int> colour_ptr, cblkL, cblkU;
@@ -275,8 +276,7 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
 void sell_fill(Handle &H, DevSell &S, const double *src);
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
 void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
-void sell_perm_in(Handle &H, DevIlu &ilu, const double *x, double *xp);
-void sell_perm_out(Handle &H, DevIlu &ilu, const double *yp, double *y);
+void sell_set_io(Handle &H, DevIlu &ilu, const double *x, double *y);
 
 // ---------------------------------------------------------------- solver.cu
 void solver_alloc(Handle &H);

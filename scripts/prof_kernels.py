@@ -17,7 +17,8 @@ e.set_solution(x)
 e.set_dirichlet_values(prob.dirichlet_values(bench.DT))
 e.assemble_first(bench.DT)
 e.precond_init()
-for k in ("assemble_step", "spmv_F", "spmv_system", "ilu_F", "spmv_S", "ilu_S", "dot", "axpy"):
+kernels = sys.argv[4].split(",") if len(sys.argv) > 4 else ["assemble_step", "spmv_F", "spmv_system", "ilu_F", "spmv_S", "ilu_S", "dot", "axpy", "add_and_dot"]
+for k in kernels:
     ms, b = e.bench_kernel(k, iters=iters, flush_l2=True)
     print(f"{k:14s} {ms:9.4f} ms  {b/1e6:10.1f} MB  {b/ms/1e6:8.1f} GB/s", flush=True)
 print("levels", [e.stat(k) for k in ("levels_F_fwd","levels_F_bwd","levels_S_fwd","levels_S_bwd")])
