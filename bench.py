@@ -169,10 +169,11 @@ def run_gpu(args):
             uid[0] = Engine.unique_id()
         dist.broadcast_object_list(uid, src=0)
         prob = DistributedNavierStokes(mesh, "3d", T=1.0, deltat=DT, test_case=2, device=local_rank, nranks=world,
-                                       rank=rank, unique_id=uid[0], ilu_ordering=args.ilu_ordering)
+                                       rank=rank, unique_id=uid[0], ilu_ordering=args.ilu_ordering,
+                                       orthogonalisation=args.orthogonalisation)
     else:
         prob = NavierStokes(mesh, "3d", T=1.0, deltat=DT, test_case=2, device=local_rank,
-                            ilu_ordering=args.ilu_ordering)
+                            ilu_ordering=args.ilu_ordering, orthogonalisation=args.orthogonalisation)
     prob.setup()
     e = prob.engine
     n_dofs_global = prob.N_global if world > 1 else prob.N
@@ -263,6 +264,8 @@ def run_gpu(args):
                            n_cells=int(mesh.n_cells), variant="NavierStokes3D", preconditioner="Yosida",
                            deltat=DT, quadrature="QGaussSimplex(3) / Witherden-Vincent 14 pt",
                            ilu_ordering={0: "natural (reference replay)", 1: "multicolour (throughput mode)"}[args.ilu_ordering],
+                           orthogonalisation={0: "modified Gram-Schmidt (reference replay)",
+                                              1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
                                      "timings flush L2 between launches",
                            partition=f"{world} subdomain(s), coordinate bisection"),
@@ -291,6 +294,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ilu-ordering", type=int, default=1, choices=[0, 1],
                     help="0: natural row order (reference replay), 1: multicolour ILU(0) (throughput mode, default)")
+    ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
+                    help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -86,7 +86,11 @@ typedef struct nsb_params {
                               1: greedy multicolour ordering of the ILU(0) factors (throughput mode;
                               a different but equally valid ILU(0), like a different mpirun -n P).
                               Must be set before nsb_finalize_setup. */
-  int32_t reserved[7];
+  int32_t orthogonalisation; /* 0: modified Gram-Schmidt exactly as SolverGMRES (replay mode),
+                              1: batched classical Gram-Schmidt (throughput mode): all coefficients of one
+                              Arnoldi step from ONE fused multi-dot kernel and one all-reduce; inner solves
+                              re-orthogonalise on deal.II's loss test, the outer solve always does two passes */
+  int32_t reserved[6];
 } nsb_params;
 
 /* Fill *p with the reference's literals for the given variant. */

@@ -193,11 +193,15 @@ __global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10)) assemble_step_q_ke
 // assemble_time_step, tensor-contracted form: the q loop is folded into a constant reference
 // tensor (exactly the same finite sum, re-associated), leaving N2*DIM*N2 FMAs per local row.
 // ---------------------------------------------------------------------------------------------
+// Persistent: a block loads the reference tensor into shared memory ONCE and then walks over groups
+// of 32 cells (ncu of the one-group-per-block version: 45% of the L1 wavefront budget went into
+// 64-bit shared loads of T and every block re-packed the 24 KB tensor).  T rows are read as 128-bit
+// broadcasts (two j per load).
 template <int DIM>
-__global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10)) assemble_step_t_kernel(AsmArgs a)
+__global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10), 3) assemble_step_t_kernel(AsmArgs a, int n_groups)
 {
   constexpr int N2 = (DIM == 2) ? 6 : 10, NV1 = DIM + 1;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   // layout: T[i][a][k][j] (N2*N2*DIM*N2) | Mh[N2][N2] | sU[N2][DIM][32] | sUt[N2][DIM][32] | sX[NV1*DIM][32]
   double *sT = smem;
   double *sMh = sT + N2 * N2 * DIM * N2;
@@ -205,7 +209,6 @@ __global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10)) assemble_step_t_ke
   double(*sUt)[DIM][32] = reinterpret_cast<double(*)[DIM][32]>(sMh + N2 * N2 + N2 * DIM * 32);
   double(*sX)[32] = reinterpret_cast<double(*)[32]>(sMh + N2 * N2 + 2 * N2 * DIM * 32);
   const int lane = threadIdx.x, i = threadIdx.y;
-  const int64_t g = blockIdx.x;
   {
     const int tid = i * 32 + lane, nthr = 32 * N2;
     // StepTensor::T is [10][10][10][3] = [i][j][a][k]; re-pack to [i][a][k][j]
@@ -215,55 +218,64 @@ __global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10)) assemble_step_t_ke
     }
     for (int idx = tid; idx < N2 * N2; idx += nthr) sMh[idx] = a.tensor->Mh[idx / N2][idx % N2];
   }
-  const int node_i = a.cell_nodes[(g * N2 + i) * 32 + lane];
-  stage_cell<DIM>(a, g, lane, i, node_i, sU, sX);
-  __syncthreads();
-  double Jinv[DIM][DIM];
-  double det = 1.0;
-  if (node_i >= 0) {
-    det = affine_inverse<DIM>(sX, lane, Jinv);
+  const double2 *Ti = reinterpret_cast<const double2 *>(sT + i * (N2 * DIM * N2));
+  for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int node_i = a.cell_nodes[(g * N2 + i) * 32 + lane];
+    __syncthreads(); // the previous group's readers of sU / sUt / sX are done (and T is in place)
+    stage_cell<DIM>(a, g, lane, i, node_i, sU, sX);
+    __syncthreads();
+    double Jinv[DIM][DIM];
+    double det = 1.0;
+    if (node_i >= 0) {
+      det = affine_inverse<DIM>(sX, lane, Jinv);
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      double s = 0.0;
+      for (int k = 0; k < DIM; ++k) {
+        double s = 0.0;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) s += Jinv[k][d] * sU[i][d][lane];
-      sUt[i][k][lane] = s * det;
+        for (int d = 0; d < DIM; ++d) s += Jinv[k][d] * sU[i][d][lane];
+        sUt[i][k][lane] = s * det;
+      }
     }
-  }
-  __syncthreads();
-  if (node_i < 0 || node_i >= a.n_nodes_owned) return;
-  double acc[N2];
+    __syncthreads();
+    if (node_i < 0 || node_i >= a.n_nodes_owned) continue;
+    // the scatter positions are independent of the arithmetic: request them first
+    int pos[N2];
+    const int *map = a.mapF + (g * (N2 * N2) + i * N2) * 32 + lane;
 #pragma unroll
-  for (int j = 0; j < N2; ++j) acc[j] = 0.0;
-  const double *Ti = sT + i * (N2 * DIM * N2);
+    for (int j = 0; j < N2; ++j) pos[j] = __ldcs(map + j * 32);
+    double acc[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) acc[j] = 0.0;
 #pragma unroll 2
-  for (int n = 0; n < N2; ++n) {
+    for (int n = 0; n < N2; ++n) {
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      const double ut = sUt[n][k][lane];
-      const double *Tr = Ti + (n * DIM + k) * N2;
+      for (int k = 0; k < DIM; ++k) {
+        const double ut = sUt[n][k][lane];
+        const double2 *Tr = Ti + (n * DIM + k) * (N2 / 2);
 #pragma unroll
-      for (int j = 0; j < N2; ++j) acc[j] += Tr[j] * ut;
+        for (int jj = 0; jj < N2 / 2; ++jj) {
+          const double2 t = Tr[jj];
+          acc[2 * jj] += t.x * ut;
+          acc[2 * jj + 1] += t.y * ut;
+        }
+      }
     }
+    double rhs[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) rhs[d] = 0.0;
+#pragma unroll
+    for (int n = 0; n < N2; ++n) {
+      const double m = sMh[i * N2 + n];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) rhs[d] += m * sU[n][d][lane];
+    }
+#pragma unroll
+    for (int j = 0; j < N2; ++j)
+      if (pos[j] >= 0) atomicAdd(a.F + pos[j], acc[j]);
+    const double sc = det * a.inv_dt;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) atomicAdd(a.rhs + int64_t(DIM) * node_i + d, rhs[d] * sc);
   }
-  double rhs[DIM];
-#pragma unroll
-  for (int d = 0; d < DIM; ++d) rhs[d] = 0.0;
-#pragma unroll
-  for (int n = 0; n < N2; ++n) {
-    const double m = sMh[i * N2 + n];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) rhs[d] += m * sU[n][d][lane];
-  }
-  const int *map = a.mapF + (g * (N2 * N2) + i * N2) * 32 + lane;
-#pragma unroll
-  for (int j = 0; j < N2; ++j) {
-    const int pos = map[j * 32];
-    if (pos >= 0) atomicAdd(a.F + pos, acc[j]);
-  }
-  const double sc = det * a.inv_dt;
-#pragma unroll
-  for (int d = 0; d < DIM; ++d) atomicAdd(a.rhs + int64_t(DIM) * node_i + d, rhs[d] * sc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -508,7 +520,7 @@ void launch_assemble_step(Handle &H, double *F_target)
   } else {
     if (H.dim == 2) {
       const size_t sm = sizeof(double) * (6 * 6 * 2 * 6 + 36 + 2 * 6 * 2 * 32 + 3 * 2 * 32);
-      assemble_step_t_kernel<2><<<groups, dim3(32, 6), sm, s>>>(a);
+      assemble_step_t_kernel<2><<<std::min(groups, 148u * 5u), dim3(32, 6), sm, s>>>(a, int(groups));
     } else {
       const size_t sm = sizeof(double) * (10 * 10 * 3 * 10 + 100 + 2 * 10 * 3 * 32 + 4 * 3 * 32);
       static bool attr_set = false;
@@ -516,7 +528,7 @@ void launch_assemble_step(Handle &H, double *F_target)
         NSB_CUDA(cudaFuncSetAttribute(assemble_step_t_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
         attr_set = true;
       }
-      assemble_step_t_kernel<3><<<groups, dim3(32, 10), sm, s>>>(a);
+      assemble_step_t_kernel<3><<<std::min(groups, 148u * 3u), dim3(32, 10), sm, s>>>(a, int(groups));
     }
   }
   NSB_CUDA(cudaGetLastError());

@@ -16,6 +16,7 @@
 // Rows of one colour are mutually independent, so inside a colour they are sorted by length
 // (no padding waste) without changing the ILU(0) factors.
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "nsb_internal.hpp"
@@ -40,8 +41,10 @@ __global__ void k_set_io(TrsvIo *io, const double *x, double *y) { io->x = x; io
 //                                                  staging in factor order, x the caller's vector:
 //                                                  the permutation is fused into the sweep)
 // MODE 2: y[4r+d]  = y*dinv - sum, also stored to out[3 order[r]+d]   (backward substitution)
-template <int MODE>
-__global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__restrict__ slice_ptr,
+// U: depth of the (col, val) software pipeline.  PAD (MODE 0 only): gather from the padded copy of x
+// (one 256-bit load per entry) or straight from the caller's vector (three 64-bit loads, no copy pass).
+template <int MODE, int U = 4, bool PAD = true>
+__global__ void __launch_bounds__(256, U == 4 ? (MODE == 0 ? 6 : 5) : 3) k_sell3(int s0, int s1, const int *__restrict__ slice_ptr,
                                                const int *__restrict__ rowid, const int *__restrict__ col,
                                                const double *__restrict__ val, const double *xp, double *y,
                                                const double *__restrict__ dinv, const int *__restrict__ order = nullptr,
@@ -56,11 +59,22 @@ __global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__rest
     const int len = (slice_ptr[s + 1] - base) >> 5;
     const int r = rowid[(int64_t(s) << 5) + lane];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    // row-local operands of the triangular sweeps are requested before the entry loop so that their
+    // latency (order -> x) overlaps it
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, di = 1.0;
+    int ro = 0;
+    if (MODE != 0 && r >= 0) {
+      ro = order[r];
+      if (MODE == 1) {
+        const double *xi = io->x + 3 * int64_t(ro);
+        b0 = xi[0]; b1 = xi[1]; b2 = xi[2];
+      } else
+        di = dinv[r];
+    }
     const int *cp = col + base + lane;
     const double *vp = val + base + lane;
     // software pipeline: the colind/val loads of the next group of U entries are issued before the
     // gathers of the current group, so one memory round trip covers U entries
-    constexpr int U = 4;
     int c[U], nc[U];
     double v[U], nv[U];
 #pragma unroll
@@ -79,7 +93,8 @@ __global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__rest
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         double x0, x1, x2;
-        ld256(xp + 4 * int64_t(c[u]), x0, x1, x2);
+        if (PAD) ld256(xp + 4 * int64_t(c[u]), x0, x1, x2);
+        else { const double *xb = xp + 3 * int64_t(c[u]); x0 = xb[0]; x1 = xb[1]; x2 = xb[2]; }
         a0 += v[u] * x0;
         a1 += v[u] * x1;
         a2 += v[u] * x2;
@@ -94,13 +109,11 @@ __global__ void __launch_bounds__(256) k_sell3(int s0, int s1, const int *__rest
       } else {
         double *o = y + 4 * int64_t(r);
         if (MODE == 1) {
-          const double *xi = io->x + 3 * int64_t(order[r]);
-          o[0] = xi[0] - a0; o[1] = xi[1] - a1; o[2] = xi[2] - a2; o[3] = 0.0;
+          o[0] = b0 - a0; o[1] = b1 - a1; o[2] = b2 - a2; o[3] = 0.0;
         } else {
-          const double di = dinv[r];
           const double r0 = o[0] * di - a0, r1 = o[1] * di - a1, r2 = o[2] * di - a2;
           o[0] = r0; o[1] = r1; o[2] = r2;
-          double *yo = io->y + 3 * int64_t(order[r]);
+          double *yo = io->y + 3 * int64_t(ro);
           yo[0] = r0; yo[1] = r1; yo[2] = r2;
         }
       }
@@ -187,42 +200,71 @@ void sell_fill(Handle &H, DevSell &S, const double *src)
 
 static inline unsigned sell_grid(int n_slices) { return unsigned(std::max(1, (n_slices + 7) / 8)); }
 
-// y_u = F_s x_u (3D).  x is copied once into the padded staging vector.
+static int env_int(const char *name, int def)
+{
+  const char *e = getenv(name);
+  return e ? atoi(e) : def;
+}
+
+// y_u = F_s x_u (3D).  Default: x is copied once into the padded staging vector (k_pad3) and gathered
+// with one 256-bit load per entry.  NSB_SPMV_PAD=0 gathers the three components straight from x when
+// the vector has no ghost offset (single rank); NSB_SELL_U picks the pipeline depth (4 | 8).
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u)
 {
   if (H.sellF_dirty) {
     sell_fill(H, H.sellF, H.Fs.val.p);
     H.sellF_dirty = false;
   }
+  static const int depth = env_int("NSB_SELL_U", 4), pad = env_int("NSB_SPMV_PAD", 1);
   const int nn = H.n_nodes;
+  const DevSell &S = H.sellF;
+  const unsigned g = sell_grid(S.n_slices);
+  if (!pad && H.n_nodes == H.n_nodes_owned) {
+    if (depth == 8)
+      k_sell3<0, 8, false><<<g, 256, 0, H.stream>>>(0, S.n_slices, S.slice_ptr.p, S.rowid.p, S.col.p, S.val.p, x_u, y_u, nullptr);
+    else
+      k_sell3<0, 4, false><<<g, 256, 0, H.stream>>>(0, S.n_slices, S.slice_ptr.p, S.rowid.p, S.col.p, S.val.p, x_u, y_u, nullptr);
+    NSB_CUDA(cudaGetLastError());
+    H.launches += 1;
+    return;
+  }
   k_pad3<<<unsigned(std::min((nn * 4 + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(nn, H.n_nodes_owned, goff_u, x_u,
                                                                                   H.d_xpad.p);
-  k_sell3<0><<<sell_grid(H.sellF.n_slices), 256, 0, H.stream>>>(0, H.sellF.n_slices, H.sellF.slice_ptr.p,
-                                                                H.sellF.rowid.p, H.sellF.col.p, H.sellF.val.p,
-                                                                H.d_xpad.p, y_u, nullptr);
+  if (depth == 8)
+    k_sell3<0, 8><<<g, 256, 0, H.stream>>>(0, S.n_slices, S.slice_ptr.p, S.rowid.p, S.col.p, S.val.p, H.d_xpad.p, y_u, nullptr);
+  else
+    k_sell3<0, 4><<<g, 256, 0, H.stream>>>(0, S.n_slices, S.slice_ptr.p, S.rowid.p, S.col.p, S.val.p, H.d_xpad.p, y_u, nullptr);
   NSB_CUDA(cudaGetLastError());
   H.launches += 2;
 }
 
-// in-place triangular solves on the padded staging vector (permuted index space)
 // yp: padded staging (factor order).  The caller's in / out vectors come through ilu.io (sell_set_io).
 // Colour 0 has no lower part (zero-length slices): its forward launch is the fused permutation.
 void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
 {
   const int nc = int(ilu.colour_ptr.size()) - 1;
   const TrsvIo *io = reinterpret_cast<const TrsvIo *>(ilu.io.p);
+  static const int depth = env_int("NSB_SELL_U", 4);
   for (int c = 0; c < nc; ++c) {
     const int a = ilu.sellL.range_slice[c], b = ilu.sellL.range_slice[c + 1];
     if (b <= a) continue;
-    k_sell3<1><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellL.slice_ptr.p, ilu.sellL.rowid.p, ilu.sellL.col.p,
-                                               ilu.sellL.val.p, yp, yp, nullptr, ilu.order.p, io);
+    if (depth == 8)
+      k_sell3<1, 8><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellL.slice_ptr.p, ilu.sellL.rowid.p, ilu.sellL.col.p,
+                                                    ilu.sellL.val.p, yp, yp, nullptr, ilu.order.p, io);
+    else
+      k_sell3<1, 4><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellL.slice_ptr.p, ilu.sellL.rowid.p, ilu.sellL.col.p,
+                                                    ilu.sellL.val.p, yp, yp, nullptr, ilu.order.p, io);
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int a = ilu.sellU.range_slice[c], b = ilu.sellU.range_slice[c + 1];
     if (b <= a) continue;
-    k_sell3<2><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellU.slice_ptr.p, ilu.sellU.rowid.p, ilu.sellU.col.p,
-                                               ilu.sellU.val.p, yp, yp, ilu.dinv.p, ilu.order.p, io);
+    if (depth == 8)
+      k_sell3<2, 8><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellU.slice_ptr.p, ilu.sellU.rowid.p, ilu.sellU.col.p,
+                                                    ilu.sellU.val.p, yp, yp, ilu.dinv.p, ilu.order.p, io);
+    else
+      k_sell3<2, 4><<<sell_grid(b - a), 256, 0, s>>>(a, b, ilu.sellU.slice_ptr.p, ilu.sellU.rowid.p, ilu.sellU.col.p,
+                                                    ilu.sellU.val.p, yp, yp, ilu.dinv.p, ilu.order.p, io);
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());

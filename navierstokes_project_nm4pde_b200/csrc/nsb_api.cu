@@ -104,7 +104,7 @@ extern "C" int nsb_create(nsb_handle *out, int dim, int device_id, int nranks, i
     NSB_CUDA(cudaMallocHost((void **)&H.h_pinned, sizeof(double) * 256));
     NSB_CUDA(cudaEventCreate(&H.ev0));
     NSB_CUDA(cudaEventCreate(&H.ev1));
-    H.d_scratch.alloc(64 + 1024 + 8);
+    H.d_scratch.alloc(64 + 1024 + 8 + 9 * 1024 + 8); // dbar | dot partials | ticket | multi-dot partials | ticket
     H.d_scratch.zero();
     NSB_CUDA(cudaDeviceSynchronize());
     halo_create(H, unique_id);
@@ -133,6 +133,8 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
     if (p->precond_type < 0 || p->precond_type > 3) throw ArgError("Invalid preconditioner type");
     if (p->gmres_tmp < 3 || p->gmres_tmp > 200) throw ArgError("nsb_set_params: gmres_tmp out of range");
     if (p->ilu_ordering < 0 || p->ilu_ordering > 1) throw ArgError("nsb_set_params: ilu_ordering must be 0 or 1");
+    if (p->orthogonalisation < 0 || p->orthogonalisation > 1)
+      throw ArgError("nsb_set_params: orthogonalisation must be 0 or 1");
     if (H.finalized && p->ilu_ordering != H.prm.ilu_ordering)
       throw StateError("nsb_set_params: ilu_ordering must be chosen before nsb_finalize_setup");
     if (!(p->deltat > 0) || !(p->nu > 0)) throw ArgError("nsb_set_params: nu and deltat must be positive");

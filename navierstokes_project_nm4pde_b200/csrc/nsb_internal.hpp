@@ -253,6 +253,11 @@ void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out
 // vv += sign * (*a_dev) * v_prev ; out_dev = vv . v_next      (SolverGMRES add_and_dot)
 void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
                          const double *v_next, double *out_dev);
+// batched classical Gram-Schmidt pieces: h[j] = vv . V_j (j < nv), *self = vv . vv ; vv -= sum h[j] V_j
+void vec_multi_dot_dev(Handle &H, int n, const double *vv, const double *V, size_t ld, int nv, double *h_dev,
+                       double *self_dev);
+void vec_multi_axpy_dev(Handle &H, int n, double *vv, const double *V, size_t ld, int nv, const double *h_dev,
+                        double *norm2_dev);
 void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering);
 void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val);
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y); // y = U^-1 D^-1 L^-1 x

@@ -114,11 +114,15 @@ static void givens_rotation(double *h, double *b, double *ci, double *si, int co
 
 // SolverGMRES::solve.  V: n_tmp basis vectors (stride sp.ld, zero-initialised by the caller at the
 // start of a solve like freshly allocated deal.II temporaries); scal: >= n_tmp + 4 device doubles.
-static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, int n_tmp, double *scal, Control &ctl)
+// orth: 0 = modified Gram-Schmidt as in deal.II; 1 = batched classical Gram-Schmidt with deal.II's
+// loss-of-orthogonality test applied to every vector; 2 = batched classical Gram-Schmidt, always two
+// passes (CGS2).
+static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, int n_tmp, double *scal, Control &ctl,
+                 int orth = 0)
 {
   const int n = sp.n_owned;
   std::vector<double> Hm(size_t(n_tmp) * (n_tmp - 1), 0.0), gamma(n_tmp + 1, 0.0), ci(n_tmp, 0.0), si(n_tmp, 0.0),
-      h(n_tmp + 2, 0.0), hh(n_tmp + 4, 0.0);
+      h(n_tmp + 2, 0.0), hh(std::max(n_tmp + 4, 64), 0.0);
   const int ldh = n_tmp - 1;
   double *v = V;
   double *p = V + size_t(n_tmp - 1) * sp.ld;
@@ -141,6 +145,48 @@ static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, in
       sp.A(V + size_t(inner) * sp.ld, 0, p);
       sp.P(p, vv);
       dim = inner + 1;
+      if (orth != 0) {
+        // batched classical Gram-Schmidt: hd[0..dim-1] = V^T vv and hd[dim] = |vv|^2 from one fused
+        // multi-dot (one all-reduce), vv -= V hd with the new |vv|^2 in hd[dim+1] (one all-reduce)
+        double *hd = scal, *hd2 = scal + 32;
+        vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd, hd + dim);
+        H.cnt_dot++;
+        if (H.nranks > 1) halo_allreduce(H, hd, dim + 1);
+        vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd, orth == 2 ? nullptr : hd + dim + 1);
+        bool second = (orth == 2);
+        if (!second) {
+          if (H.nranks > 1) halo_allreduce(H, hd + dim + 1, 1);
+          reduce_fetch(H, hd, dim + 2, hh.data());
+          for (int i = 0; i < dim; ++i) h[i] = hh[i];
+          // deal.II's test (solver_gmres.h, modified_gram_schmidt) on every vector
+          second = !(std::sqrt(hh[dim + 1]) > 10.0 * std::sqrt(hh[dim]) * std::sqrt(2.220446049250313e-16));
+        }
+        double s2 = hh[dim + 1];
+        if (second) {
+          vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, nullptr);
+          H.cnt_dot++;
+          if (H.nranks > 1) halo_allreduce(H, hd2, dim);
+          vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, hd2 + dim);
+          if (H.nranks > 1) halo_allreduce(H, hd2 + dim, 1);
+          if (orth == 2) {
+            reduce_fetch(H, scal, 64, hh.data());
+            for (int i = 0; i < dim; ++i) h[i] = hh[i] + hh[32 + i];
+            s2 = hh[32 + dim];
+          } else {
+            reduce_fetch(H, hd2, dim + 1, hh.data());
+            for (int i = 0; i < dim; ++i) h[i] += hh[i];
+            s2 = hh[dim];
+          }
+        }
+        const double s = std::sqrt(s2);
+        h[inner + 1] = s;
+        if (s != 0.0) vec_scale(H, n, 1.0 / s, vv);
+        givens_rotation(h.data(), gamma.data(), ci.data(), si.data(), inner);
+        for (int i = 0; i < dim; ++i) Hm[size_t(i) * ldh + inner] = h[i];
+        rho = std::fabs(gamma[dim]);
+        state = ctl.check(accumulated, rho);
+        continue;
+      }
       // modified_gram_schmidt: all coefficients stay on the device until the single fetch below
       const bool consider = (!re_orth) && (inner % 5 == 4);
       double *hd = scal;              // hd[0..dim-1] coefficients, hd[dim] = |vv|^2 after orthogonalisation
@@ -289,7 +335,7 @@ static void inner_gmres_F(Handle &H, double *x, int goff_x, const double *b, dou
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluF, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
   NSB_CUDA(cudaMemsetAsync(w.V_inner.p, 0, sizeof(double) * size_t(sp.ld) * H.prm.gmres_tmp, H.stream));
-  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl);
+  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_F += ctl.last_step;
   H.n_F_solves++;
 }
@@ -304,7 +350,7 @@ static void inner_gmres_S(Handle &H, double *x, int goff_x, const double *b, dou
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluS, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
   NSB_CUDA(cudaMemsetAsync(w.V_inner.p, 0, sizeof(double) * size_t(sp.ld) * H.prm.gmres_tmp, H.stream));
-  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl);
+  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_S += ctl.last_step;
   H.n_S_solves++;
 }
@@ -446,7 +492,8 @@ int solve_outer(Handle &H)
   sp.P = [&H](const double *r, double *z) { precond_vmult(H, r, z); };
   Control ctl{H.prm.outer_maxit, H.prm.outer_tol};
   NSB_CUDA(cudaMemsetAsync(w.V_outer.p, 0, sizeof(double) * size_t(sp.ld) * H.prm.gmres_tmp, H.stream));
-  const int rc = gmres(H, sp, H.d_sol.p, H.d_rhs.p, w.V_outer.p, H.prm.gmres_tmp, w.scal.p, ctl);
+  const int rc = gmres(H, sp, H.d_sol.p, H.d_rhs.p, w.V_outer.p, H.prm.gmres_tmp, w.scal.p, ctl,
+                       H.prm.orthogonalisation ? 2 : 0);
   H.last_outer = ctl.last_step;
   H.last_res = ctl.last_value;
   return rc;

@@ -189,6 +189,7 @@ typedef struct nso_ctx {
   int *order_u, *order_p; /* optional ILU orderings (performance mode of the engine), NULL = natural */
   /* solver settings */
   int gmres_tmp;            /* max_n_tmp_vectors, deal.II default 30 */
+  int orthogonalisation;    /* 0: MGS (deal.II); 1: batched classical GS (engine throughput mode) */
   double outer_tol;         /* 1e-4 absolute (src/NavierStokes2D.cpp:535) */
   int outer_maxit;
   double inner_rtol;        /* 1e-2 (Preconditioners.hpp:260) */
@@ -338,6 +339,8 @@ NSO_API void nso_set_options(nso_ctx *c, int dirichlet_mode, int gmres_tmp, doub
   if (inner_rtol > 0) c->inner_rtol = inner_rtol;
   if (inner_maxit > 0) c->inner_maxit = inner_maxit;
 }
+
+NSO_API void nso_set_orthogonalisation(nso_ctx *c, int mode) { c->orthogonalisation = mode; }
 
 NSO_API double *nso_ptr(nso_ctx *c, const char *name)
 {
@@ -864,6 +867,9 @@ typedef struct {
   nso_ctx *hist;
   /* block split for BlockVector reductions (nb = 0: plain vector) */
   int nb;
+  /* 0: modified Gram-Schmidt (deal.II); 1: classical Gram-Schmidt + deal.II's loss test on every
+     vector; 2: classical Gram-Schmidt, always two passes (the engine's throughput mode) */
+  int orth;
 } control_t;
 
 static void hist_push(nso_ctx *c, double r)
@@ -943,6 +949,28 @@ static int gmres_solve(int n, op_fn A, void *Actx, op_fn P, void *Pctx, double *
       A(Actx, V + (size_t)inner * n, p);
       P(Pctx, p, vv);
       dim = inner + 1;
+      if (ctl->orth != 0) { /* batched classical Gram-Schmidt (engine: nsb_params.orthogonalisation = 1) */
+        double *hh = (double *)xcalloc(dim, sizeof(double));
+        double n0 = bdot(n, nb, vv, vv);
+        for (int i = 0; i < dim; ++i) h[i] = bdot(n, nb, vv, V + (size_t)i * n);
+        for (int i = 0; i < dim; ++i) vaxpy(n, -h[i], V + (size_t)i * n, vv);
+        double s2 = bdot(n, nb, vv, vv);
+        int second = (ctl->orth == 2) || !(sqrt(s2) > 10.0 * sqrt(n0) * sqrt(2.220446049250313e-16));
+        if (second) {
+          for (int i = 0; i < dim; ++i) hh[i] = bdot(n, nb, vv, V + (size_t)i * n);
+          for (int i = 0; i < dim; ++i) { vaxpy(n, -hh[i], V + (size_t)i * n, vv); h[i] += hh[i]; }
+          s2 = bdot(n, nb, vv, vv);
+        }
+        free(hh);
+        const double s = sqrt(s2);
+        h[inner + 1] = s;
+        if (s != 0.0) vscale(n, 1.0 / s, vv);
+        givens_rotation(h, gamma, ci, si, inner);
+        for (int i = 0; i < dim; ++i) H[(size_t)i * ldh + inner] = h[i];
+        rho = fabs(gamma[dim]);
+        state = control_check(ctl, accumulated, rho);
+        continue;
+      }
       /* modified_gram_schmidt */
       double norm_vv_start = 0.0;
       const int consider = (!re_orth) && (inner % 5 == 4);
@@ -1054,6 +1082,7 @@ static void inner_gmres(nso_ctx *c, const csr_t *A, ilu_t *ilu, double *x, const
   control_t ctl;
   memset(&ctl, 0, sizeof(ctl));
   ctl.maxit = c->inner_maxit; ctl.tol = tol;
+  ctl.orth = c->orthogonalisation ? 1 : 0;
   gmres_solve(A->n_rows, op_csr, (void *)A, ilu_apply, ilu, x, b, c->gmres_tmp, &ctl);
   if (is_F) { c->n_inner_F += ctl.last_step; c->n_F_solves++; }
   else { c->n_inner_S += ctl.last_step; c->n_S_solves++; }
@@ -1245,6 +1274,7 @@ NSO_API int nso_solve_step(nso_ctx *c, int ptype, int *outer_its, double *last_r
   control_t ctl;
   memset(&ctl, 0, sizeof(ctl));
   ctl.maxit = c->outer_maxit; ctl.tol = c->outer_tol; ctl.hist = c; ctl.nb = c->nu;
+  ctl.orth = c->orthogonalisation ? 2 : 0;
   op_fn P = ptype == 0 ? yosida_vmult : ptype == 1 ? simple_vmult : ptype == 2 ? ayosida_vmult : asimple_vmult;
   const int rc = gmres_solve(c->N, op_system, c, P, c, c->sol_owned, c->rhs, c->gmres_tmp, &ctl);
   if (outer_its) *outer_its = ctl.last_step;

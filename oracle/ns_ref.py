@@ -426,6 +426,10 @@ class Oracle:
         self.L.nso_set_options(self.h, dirichlet_mode, gmres_tmp, C.c_double(outer_tol), outer_maxit,
                                C.c_double(inner_rtol), inner_maxit)
 
+    def set_orthogonalisation(self, mode):
+        """0: modified Gram-Schmidt (deal.II); 1: batched classical Gram-Schmidt (engine throughput mode)."""
+        self.L.nso_set_orthogonalisation(self.h, int(mode))
+
     def set_dirichlet(self, rows, vals):
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         vals = np.ascontiguousarray(vals, dtype=np.float64)

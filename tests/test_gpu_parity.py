@@ -275,3 +275,71 @@ def test_multicolour_ilu_mode(case_name, ptype):
         assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < FIELD_TOL, step
     # far fewer dependency levels than the natural ordering
     assert e.stat("levels_F_fwd") <= 40 and e.stat("levels_S_fwd") <= 80
+
+
+@pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cyl3d", "yosida"),
+                                             ("cube", "yosida")])
+def test_batched_gram_schmidt_mode(case_name, ptype):
+    """Throughput mode of the Krylov solvers (orthogonalisation = 1): classical Gram-Schmidt with all
+    coefficients of an Arnoldi step from one fused multi-dot (inner solves: deal.II's loss test on
+    every vector; outer solve: two passes), on top of the multicolour ILU(0).  Checked against the
+    oracle running the same variant: same iteration counts, fields within 1e-8."""
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1, orthogonalisation=1)
+    o.set_ilu_order(*_oracle_order(case, e))
+    o.set_orthogonalisation(1)
+    rows, vals = case.bc(0.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    x0 = case.initial()
+    o.set_solution(x0)
+    e.set_solution(x0)
+    t = 0.0
+    for step in range(3):
+        t += case.dt
+        rows, vals = case.bc(t if case.variant == "conv" else 2.0 + t)
+        o.set_dirichlet_values(vals)
+        e.set_dirichlet_values(vals)
+        if case.variant == "conv":
+            neu = case.neumann(t - case.dt)
+            o.set_neumann_rhs(neu)
+            e.set_neumann_rhs(neu[: case.n_u])
+        if step == 0:
+            o.assemble_first(); e.assemble_first()
+        else:
+            o.assemble_step(); e.assemble_step()
+        rc, its_o, _ = o.solve_step(ptype)
+        its_e, _, _ = e.solve_step()
+        assert rc == 0 and its_e == its_o, (step, its_e, its_o)
+        assert e.stat("n_inner_F") == o.stat("n_inner_F")
+        xo, xe = o.array("sol_owned", case.N), e.get_solution()
+        assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < FIELD_TOL, step
+
+
+@pytest.mark.parametrize("case_name,ptype", [("cyl3d", "yosida"), ("cyl2d", "asimple")])
+def test_chunked_multicolour_ordering(case_name, ptype, monkeypatch):
+    """Chunk-major multicolour ordering (rows sorted by (chunk, colour)): the L2-blocking variant of the
+    throughput mode, here forced to tiny chunks.  Still an exact ILU(0) of the permuted matrix: the
+    oracle factorising in the same order gives the same preconditioner and the same iterations."""
+    monkeypatch.setenv("NSB_ILU_CHUNK", "97")
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1)
+    assert e.stat("levels_F_fwd") > 40  # many (chunk, colour) groups
+    o.set_ilu_order(*_oracle_order(case, e))
+    rows, vals = case.bc(2.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    e.set_dirichlet_values(vals)
+    x0 = 0.1 * case.random_state()
+    for side in (o, e):
+        side.set_solution(x0)
+        side.assemble_first()
+    o.precond_init(ptype); e.precond_init()
+    x = case.random_state()
+    xu, xp = x[: case.n_u], x[case.n_u:]
+    assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-11
+    assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-11
+    rc, its_o, _ = o.solve_step(ptype)
+    its_e, _, _ = e.solve_step()
+    assert rc == 0 and its_e == its_o
+    assert T.rel_l2(e.get_solution()[: case.n_u], o.array("sol_owned", case.N)[: case.n_u]) < FIELD_TOL

@@ -1,0 +1,122 @@
+"""Size-independent properties of the CUDA hot path at bench size (`-m gpu`).
+
+The oracle cannot follow at millions of DoFs in test time, so these checks use identities of the
+discretisation and of the solver that hold at any size, on the 2 M-DoF refined 3D cylinder
+(`bench.py` workload `cyl3d-2M`, same mesh family as BASELINE.json configs[4]) in the throughput
+configuration `bench.py` runs (multicolour ILU(0), batched Gram-Schmidt) -- i.e. through the SELL-32
+kernels that the small parity cases only touch with a handful of slices.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from navierstokes_project_nm4pde_b200 import HostMesh, NavierStokes  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+WORKLOAD = "cyl3d-2M"
+
+
+@pytest.fixture(scope="module")
+def prob():
+    s, nz = bench.WORKLOADS[WORKLOAD]
+    p = NavierStokes(HostMesh.cylinder3d(s, nz), "3d", T=1.0, deltat=bench.DT, test_case=2, ilu_ordering=1,
+                     orthogonalisation=1)
+    p.setup()
+    rng = np.random.default_rng(20240607)
+    x = np.zeros(p.N)
+    x[: p.n_u] = rng.uniform(-1.0, 1.0, p.n_u)
+    e = p.engine
+    e.set_solution(x)
+    e.set_dirichlet_values(p.dirichlet_values(bench.DT))
+    e.assemble_first(bench.DT)
+    p.rng = rng
+    return p
+
+
+def _interior_mask(p):
+    m = np.ones(p.n_u, bool)
+    m[p._dir_rows] = False
+    return m
+
+
+def test_divergence_of_constant_velocity_vanishes(prob):
+    """Block (1,0): sum_j B_ij c = int psi_i div(c) = 0 for a constant field (columns are never
+    eliminated, NavierStokes2D.cpp:354), for every one of the ~9e4 pressure rows."""
+    e = prob.engine
+    c = np.tile([0.3, -1.1, 0.7], prob.n_u // 3)
+    y = e.block_vmult("B", c)
+    scale = np.abs(e.block_vmult("B", np.abs(c))).max()
+    assert np.abs(y).max() < 1e-11 * scale
+
+
+def test_spmv_is_linear_and_blocks_compose(prob):
+    """system_matrix.vmult is linear and equals its blocks: y_u = F x_u + Bt x_p, y_p = B x_u."""
+    e, rng, nu = prob.engine, prob.rng, prob.n_u
+    x, z = rng.uniform(-1, 1, prob.N), rng.uniform(-1, 1, prob.N)
+    a, b = 0.37, -2.5
+    lhs = e.system_vmult(a * x + b * z)
+    rhs = a * e.system_vmult(x) + b * e.system_vmult(z)
+    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
+    y = e.system_vmult(x)
+    yu = e.block_vmult("F", x[:nu]) + e.block_vmult("Bt", x[nu:])
+    yp = e.block_vmult("B", x[:nu])
+    assert np.linalg.norm(y[:nu] - yu) < 1e-13 * np.linalg.norm(yu)
+    assert np.linalg.norm(y[nu:] - yp) < 1e-13 * np.linalg.norm(yp)
+
+
+def test_step_assembly_rhs_identity(prob):
+    """For a constant advecting state u = c: stiffness and convection rows sum to zero, so on every
+    unconstrained row F 1 = (M/dt) 1 and the assembled rhs = M u / dt = c (F 1) -- ties the matrix
+    scatter (atomics through mapF), the rhs and the K + C(u) composition of assemble_time_step
+    together over all 4.7e5 cells."""
+    e, nu = prob.engine, prob.n_u
+    c = np.array([0.8, -0.4, 0.25])
+    x = np.zeros(prob.N)
+    x[:nu] = np.tile(c, nu // 3)
+    saved = e.get_solution()
+    e.set_solution(x)
+    e.assemble_step(2 * bench.DT)
+    F1 = e.block_vmult("F", np.ones(nu))
+    rhs = e.get_rhs()[:nu]
+    m = _interior_mask(prob)
+    expect = np.tile(c, nu // 3) * F1
+    assert np.abs(rhs[m] - expect[m]).max() < 1e-11 * np.abs(expect[m]).max()
+    # total mass: sum_i (M 1)_i / dt over ALL rows is |Omega| / dt per component; interior rows give less
+    assert 0.0 < F1[m].sum() * bench.DT / 3.0 < 2.5 * 0.41 * 0.41
+    e.set_solution(saved)
+    e.assemble_step(2 * bench.DT)
+
+
+def test_ilu_apply_is_linear_and_a_good_inverse(prob):
+    """The multicolour SELL-32 sweeps: linear, and U^-1 D^-1 L^-1 F x ~ x for the mass-dominated F
+    (dt = 2e-4): the preconditioned operator stays within 0.5 of the identity in relative l2."""
+    e, rng, nu = prob.engine, prob.rng, prob.n_u
+    e.precond_init()
+    x, z = rng.uniform(-1, 1, nu), rng.uniform(-1, 1, nu)
+    lhs = e.ilu_apply(0, 0.5 * x - 3.0 * z)
+    rhs = 0.5 * e.ilu_apply(0, x) - 3.0 * e.ilu_apply(0, z)
+    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
+    w = e.ilu_apply(0, e.block_vmult("F", x))
+    assert np.linalg.norm(w - x) < 0.5 * np.linalg.norm(x)
+    xp = rng.uniform(-1, 1, prob.n_p)
+    ws = e.ilu_apply(1, e.block_vmult("S", xp))
+    assert np.linalg.norm(ws - xp) < 0.9 * np.linalg.norm(xp)
+
+
+def test_solve_reaches_the_reference_stopping_criterion(prob):
+    """solve_time_step: on return the preconditioned residual |P^-1 (b - A x)| is at the reference's
+    absolute tolerance 1e-4 (NavierStokes2D.cpp:535), recomputed here from the operators alone."""
+    e = prob.engine
+    its, _, _ = e.solve_step()
+    assert its > 0
+    assert e.stat("n_inner_F") > 0 and e.stat("n_F_solves") == 2 * e.stat("n_S_solves")  # Yosida: two F solves per vmult
+    x = e.get_solution()
+    r = e.get_rhs() - e.system_vmult(x)
+    z = e.precond_vmult(r)
+    # inexact inner solves (rel. 1e-2) make P^-1 a slightly different operator on every application
+    assert np.linalg.norm(z) < 5e-4

@@ -1,0 +1,80 @@
+"""CPU-only checks of the boundary and the host logic: the C-ABI library loads and exports every
+symbol include/nsb.h declares, refuses to compute without a GPU (no CPU fallback), and the host
+prerequisites (mesh generators, .msh I/O, DoF numbering, boundary lists) behave like the
+reference's setup() (NavierStokes2D.cpp:2-157)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from navierstokes_project_nm4pde_b200 import Engine, HostDofs, HostMesh, NavierStokes, _lib
+from oracle import ns_ref as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nsb.h")).read()
+    names = sorted(set(re.findall(r"\b(ns[bh]_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 60
+    lib = _lib.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    """Without a usable sm_100 device nsb_create fails loudly; nothing routes to the oracle."""
+    if Engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.NsbError) as ei:
+        Engine(2)
+    assert "no CPU fallback" in str(ei.value)
+    src = "".join(open(os.path.join(ROOT, "navierstokes_project_nm4pde_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "navierstokes_project_nm4pde_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("CPU oracle lives", "")  # the product never imports the checker
+
+
+@pytest.mark.parametrize("gen,dim,ids", [(lambda: HostMesh.cylinder2d(1), 2, {0, 1, 2, 3}),
+                                         (lambda: HostMesh.cylinder3d(1, 3), 3, {0, 1, 2, 3}),
+                                         (lambda: HostMesh.cube(3), 3, {0, 1, 2, 3, 4, 5})])
+def test_generators_and_numbering(gen, dim, ids):
+    """Boundary ids as in the .geo scripts (Cylinder2D.geo:40-43, Cylinder3D.geo:126-129,
+    mesh-cube.geo:16-21); DoF numbering = distribute_dofs + component_wise as restated by the
+    oracle's independent Python numbering."""
+    m = gen()
+    assert m.dim == dim and set(np.unique(m.bface_ids).tolist()) == ids
+    d = HostDofs(m)
+    num = R.number_dofs(dim, m.vertices, m.cells)
+    assert np.array_equal(num["cell_dofs"], d.cell_dofs())
+    assert d.n_u == num["n_u"] and d.n_p == num["n_p"] == m.n_vertices
+    # positive orientation of every cell (FEValues would otherwise see negative JxW)
+    X = m.vertices[m.cells]
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))
+    assert (np.linalg.det(J) > 0).all()
+
+
+def test_msh_roundtrip(tmp_path):
+    """GridIn::read_msh replacement: Gmsh v2 ASCII written and read back keeps cells, vertices and ids."""
+    m = HostMesh.cylinder2d(1)
+    path = str(tmp_path / "c.msh")
+    m.write_msh(path)
+    r = HostMesh.read_msh(path)
+    assert np.array_equal(m.cells, r.cells) and np.allclose(m.vertices, r.vertices, rtol=0, atol=1e-15)
+    key = lambda mm: sorted((tuple(sorted(f.tolist())), int(i)) for f, i in zip(mm.bfaces, mm.bface_ids))  # noqa: E731
+    assert key(m) == key(r)
+
+
+def test_dirichlet_lists_follow_the_reference_order():
+    """interpolate_boundary_values is called for the inlet first and the walls second, the second
+    call overwriting shared nodes with zero (NavierStokes2D.cpp:328-353)."""
+    p = NavierStokes(HostMesh.cylinder2d(1), "2d", T=1.0, deltat=0.01, test_case=3)
+    p.setup_host()
+    v = p.dirichlet_values(1.0).reshape(-1, 2)
+    xyz = p._dir_xyz
+    inlet = np.isclose(xyz[:, 0], 0.0)
+    corner = inlet & (np.isclose(xyz[:, 1], 0.0) | np.isclose(xyz[:, 1], 0.41))
+    assert (v[~inlet] == 0).all() and (v[corner] == 0).all() and (v[inlet & ~corner, 0] > 0).all()
+    assert (v[:, 1] == 0).all()
+    assert len(np.unique(p._dir_rows)) == len(p._dir_rows)

@@ -404,3 +404,33 @@ def test_ethier_steinman_orders(neumann_face_ok):
     rate_h1 = math.log2(errs[0][1] / errs[1][1])
     assert 2.5 < rate_l2 < 3.6, (errs, rate_l2)
     assert 1.6 < rate_h1 < 2.6, (errs, rate_h1)
+
+
+def test_batched_gram_schmidt_matches_modified():
+    """The oracle's classical Gram-Schmidt variant (the engine's throughput mode) is the same Krylov
+    method in exact arithmetic: tightly converged solutions agree with the MGS (deal.II) variant and
+    the loose-tolerance runs take (nearly) the same number of iterations."""
+    import os, sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import helpers as T
+
+    sols, its = [], []
+    for mode in (0, 1):
+        case = T.Case("box3d")
+        o = case.oracle()
+        o.set_orthogonalisation(mode)
+        rows, vals = case.bc(2.0)
+        o.set_dirichlet(rows, vals)
+        o.set_solution(0.1 * case.random_state())
+        o.assemble_first()
+        rc, k, _ = o.solve_step("yosida")
+        assert rc == 0
+        its.append(k)
+        o.set_options(outer_tol=1e-11, inner_rtol=1e-8)
+        o.assemble_step()
+        rc, _, _ = o.solve_step("yosida")
+        assert rc == 0
+        sols.append(o.array("sol_owned", case.N).copy())
+    assert abs(its[0] - its[1]) <= 2, its
+    assert T.rel_l2(sols[1][: case.n_u], sols[0][: case.n_u]) < 1e-7
