@@ -195,9 +195,23 @@ def run_gpu(args):
     e.set_solution(prob.initial_condition())
     tm = DT
     e.set_dirichlet_values(prob.dirichlet_values(tm))
+    # The impulsive start from u = 0 makes this the hardest solve of the run (>1000 outer iterations at
+    # 20 M DoF); it is state preparation, not part of any timed region, so it is capped at
+    # --first-step-cap outer iterations (0 = run to the reference tolerance).
+    from navierstokes_project_nm4pde_b200._lib import NsbError
+
     barrier(); t0 = time.perf_counter()
     e.assemble_first(tm)
-    its_first = e.solve_step()[0]
+    first_converged = True
+    if args.first_step_cap > 0:
+        e.set_params(outer_maxit=args.first_step_cap)
+    try:
+        its_first = e.solve_step()[0]
+    except NsbError as ex:
+        if ex.code != -4:  # NSB_ERR_NOCONV
+            raise
+        its_first, first_converged = args.first_step_cap, False
+    e.set_params(outer_maxit=100000)  # NavierStokes3D.cpp:551
     barrier(); first_step_s = time.perf_counter() - t0
     for _ in range(args.warmup):
         tm += DT
@@ -271,6 +285,7 @@ def run_gpu(args):
                            partition=f"{world} subdomain(s), coordinate bisection"),
                e2e=e2e, roofline=roofline, clocks=clocks,
                detail=dict(outer_iterations=its, first_step_s=first_step_s, first_step_iterations=its_first,
+                           first_step_converged=first_converged,
                            setup_s=setup_s, t_prec_s=t_prec, t_solve_s=t_solve, last_step_counts=stats,
                            levels={k: e.stat(k) for k in ("levels_F_fwd", "levels_F_bwd", "levels_S_fwd",
                                                            "levels_S_bwd")}))
@@ -287,7 +302,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cyl3d-20M", choices=sorted(WORKLOADS))
@@ -296,6 +311,8 @@ def main():
                     help="0: natural row order (reference replay), 1: multicolour ILU(0) (throughput mode, default)")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
+    ap.add_argument("--first-step-cap", type=int, default=560,
+                    help="outer GMRES iterations allowed in the untimed first step (20 restart cycles; 0 = unlimited)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

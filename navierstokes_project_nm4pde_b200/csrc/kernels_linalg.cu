@@ -594,9 +594,9 @@ static void level_schedule(int n, const std::vector<int> &rowptr, const std::vec
 // Greedy multicolouring in natural order, then rows sorted by (chunk, colour, natural index) where a
 // chunk is a run of `chunk_rows` consecutive rows.  Every (chunk, colour) group is an independent set
 // and only depends on groups before it, so the groups are the levels of both triangular solves.
-// Chunking keeps the part of the vector a group gathers from (its own chunk plus the interface of
-// the previous one) resident in L2 across the colour sweeps: without it every sweep re-reads the
-// gathered nodes from HBM (ncu, profiles/: 6.7 GB of DRAM traffic for 2.5 GB of algorithmic bytes).
+// Chunking was meant to keep the part of the vector a group gathers from resident in L2 across the
+// colour sweeps (without it every sweep re-reads the gathered nodes from HBM; ncu, profiles/: 6.7 GB
+// of DRAM traffic for 2.5 GB of algorithmic bytes); see ilu_chunk_rows for why it is off by default.
 static void multicolour_order(int n, const Csr &A, int n_owned_cols, int chunk_rows, std::vector<int> &order,
                               std::vector<int> &colour_ptr)
 {
@@ -630,13 +630,15 @@ static void multicolour_order(int n, const Csr &A, int n_owned_cols, int chunk_r
   if (colour_ptr.size() == 1) colour_ptr.push_back(0);
 }
 
-// rows per chunk of the multicolour ordering: NSB_ILU_CHUNK (rows; 0 = one chunk), default sized so
-// that the padded staging of a chunk (32 B per row and right-hand-side block) takes about 40 MB of L2
+// rows per chunk of the multicolour ordering: NSB_ILU_CHUNK (rows), default 0 = one chunk.  Measured
+// at 19.9 M DoF (profiles/README.md): chunks of 0.8 / 1.25 / 2.5 M nodes make the F_s apply SLOWER
+// (3.3 / 2.9 / 2.2 ms against 1.68 ms unchunked) -- the 5x more, 5x smaller sweeps are latency-bound
+// and lose more than the L2 residency of the gathered vector gains -- so chunking stays off.
 static int ilu_chunk_rows(int bs_rhs)
 {
   const char *e = getenv("NSB_ILU_CHUNK");
-  if (e) return atoi(e);
-  return bs_rhs >= 2 ? 1250000 : 5000000;
+  (void)bs_rhs;
+  return e ? atoi(e) : 0;
 }
 
 // ordering: 0 = natural local row order (what Ifpack does in the reference), 1 = multicolour.

@@ -236,8 +236,8 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
   ilu.stream = true;
   ilu.sell = false;
   if (ilu.bs_rhs == 3) { // SELL-32 copies of the factors for the 3-component solves
-    sell_build(Lp, Lc, mapL, colour_ptr, sell_window(), ilu.sellL);
-    sell_build(Up, Uc, mapU, colour_ptr, sell_window(), ilu.sellU);
+    sell_build(Lp, Lc, mapL, colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellL);
+    sell_build(Up, Uc, mapU, colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellU);
     ilu.sell = true;
   }
   (void)H;

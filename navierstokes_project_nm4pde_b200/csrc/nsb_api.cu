@@ -310,7 +310,7 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     }
     stream_build_spmv(H);
     if (dim == 3) {
-      sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, H.sellF);
+      sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, sell_lanes_for(H.hFs.n_rows), H.sellF);
       H.d_xpad.alloc(size_t(4) * H.n_nodes);
       H.d_xpad.zero();
     }

@@ -96,7 +96,7 @@ struct DevCsr {
 
 // SELL-32 storage (kernels_sell.cu)
 struct DevSell {
-  int n_slices = 0;
+  int n_slices = 0, lanes = 1;    // lanes per row (1 | 4), see k_sell3
   int64_t n_slots = 0;
   DevBuf<int> slice_ptr, rowid, col, map;
   DevBuf<double> val;
@@ -277,7 +277,8 @@ void stream_trsv(Handle &H, DevIlu &ilu, double *y, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernels_sell.cu
 void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
-                const std::vector<int> &ranges, int window, DevSell &out);
+                const std::vector<int> &ranges, int window, int lanes, DevSell &out);
+int sell_lanes_for(int n_rows);
 void sell_fill(Handle &H, DevSell &S, const double *src);
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
 void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);

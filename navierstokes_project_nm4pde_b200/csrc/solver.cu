@@ -26,6 +26,7 @@ void solver_alloc(Handle &H)
   const int nt = H.prm.gmres_tmp;
   w->V_outer.alloc(nl * nt);
   w->V_inner.alloc(std::max(nu, np) * nt);
+  w->V_inner.zero();
   for (auto &b : w->tu) b.alloc(nu);
   for (auto &b : w->tp) b.alloc(std::max<size_t>(np, 1));
   w->scal.alloc(256);
@@ -112,8 +113,8 @@ static void givens_rotation(double *h, double *b, double *ci, double *si, int co
   b[col] *= ci[col];
 }
 
-// SolverGMRES::solve.  V: n_tmp basis vectors (stride sp.ld, zero-initialised by the caller at the
-// start of a solve like freshly allocated deal.II temporaries); scal: >= n_tmp + 4 device doubles.
+// SolverGMRES::solve.  V: n_tmp basis vectors (stride sp.ld; every vector is fully written before it
+// is read, so the workspace needs no clearing between solves); scal: >= 64 device doubles.
 // orth: 0 = modified Gram-Schmidt as in deal.II; 1 = batched classical Gram-Schmidt with deal.II's
 // loss-of-orthogonality test applied to every vector; 2 = batched classical Gram-Schmidt, always two
 // passes (CGS2).
@@ -334,7 +335,6 @@ static void inner_gmres_F(Handle &H, double *x, int goff_x, const double *b, dou
   sp.A = [&H](const double *xx, int goff, double *y) { apply_F(H, xx, goff, y); };
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluF, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
-  NSB_CUDA(cudaMemsetAsync(w.V_inner.p, 0, sizeof(double) * size_t(sp.ld) * H.prm.gmres_tmp, H.stream));
   gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_F += ctl.last_step;
   H.n_F_solves++;
@@ -349,7 +349,6 @@ static void inner_gmres_S(Handle &H, double *x, int goff_x, const double *b, dou
   sp.A = [&H](const double *xx, int goff, double *y) { apply_S(H, xx, goff, y); };
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluS, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
-  NSB_CUDA(cudaMemsetAsync(w.V_inner.p, 0, sizeof(double) * size_t(sp.ld) * H.prm.gmres_tmp, H.stream));
   gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_S += ctl.last_step;
   H.n_S_solves++;

@@ -316,12 +316,14 @@ def test_batched_gram_schmidt_mode(case_name, ptype):
         assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < FIELD_TOL, step
 
 
+@pytest.mark.parametrize("lanes", [1, 4])
 @pytest.mark.parametrize("case_name,ptype", [("cyl3d", "yosida"), ("cyl2d", "asimple")])
-def test_chunked_multicolour_ordering(case_name, ptype, monkeypatch):
+def test_chunked_multicolour_ordering(case_name, ptype, lanes, monkeypatch):
     """Chunk-major multicolour ordering (rows sorted by (chunk, colour)): the L2-blocking variant of the
     throughput mode, here forced to tiny chunks.  Still an exact ILU(0) of the permuted matrix: the
     oracle factorising in the same order gives the same preconditioner and the same iterations."""
     monkeypatch.setenv("NSB_ILU_CHUNK", "97")
+    monkeypatch.setenv("NSB_SELL_LANES", str(lanes))  # both SELL-32 layouts: one / four lanes per row
     case = T.Case(case_name)
     o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1)
     assert e.stat("levels_F_fwd") > 40  # many (chunk, colour) groups
@@ -339,6 +341,8 @@ def test_chunked_multicolour_ordering(case_name, ptype, monkeypatch):
     xu, xp = x[: case.n_u], x[case.n_u:]
     assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-11
     assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-11
+    Fx = T.oracle_blocks(o, "sys")["F"] @ xu
+    assert T.rel_l2(e.block_vmult("F", xu), Fx) < 1e-13
     rc, its_o, _ = o.solve_step(ptype)
     its_e, _, _ = e.solve_step()
     assert rc == 0 and its_e == its_o
