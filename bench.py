@@ -282,7 +282,8 @@ def run_gpu(args):
                                               1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
                                      "timings flush L2 between launches",
-                           partition=f"{world} subdomain(s), coordinate bisection"),
+                           partition=f"{world} subdomain(s), coordinate bisection",
+                           transport=(getattr(prob, "transport", "none") if world > 1 else "none")),
                e2e=e2e, roofline=roofline, clocks=clocks,
                detail=dict(outer_iterations=its, first_step_s=first_step_s, first_step_iterations=its_first,
                            first_step_converged=first_converged,

@@ -134,6 +134,15 @@ int nsb_set_halo(nsb_handle h, int32_t n_neighbours, const int32_t *neighbour_ra
                  const int32_t *send_node_ptr, const int32_t *send_node_idx, const int32_t *recv_node_cnt,
                  const int32_t *send_p_ptr, const int32_t *send_p_idx, const int32_t *recv_p_cnt);
 
+/* Peer-memory transport over NVLink (replaces MPI point-to-point / MPI_Allreduce of the Epetra layer
+ * with direct stores into the peers' HBM, see csrc/halo.cu).  After nsb_set_halo every rank calls
+ * nsb_p2p_export (fills a 64-byte cudaIpcMemHandle of its mailbox), the caller all-gathers the
+ * handles in rank order (MPI_Allgather / torch.distributed) and hands them to nsb_p2p_attach.
+ * Without these two calls, or when peer mapping fails (negative return), the handle keeps using NCCL.
+ * nsb_stat(h, "p2p") tells which transport is active. */
+int nsb_p2p_export(nsb_handle h, void *handle64);
+int nsb_p2p_attach(nsb_handle h, const void *handles /* nranks * 64 bytes */);
+
 /* ---- boundary data -------------------------------------------------------------------- */
 /* replaces: VectorTools::interpolate_boundary_values (src/NavierStokes2D.cpp:328-353): rows are
  * velocity DoF indices (local, owned); all components of a node must be listed (the

@@ -42,6 +42,8 @@ SIGNATURES = {
     "nsb_get_pattern_size": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nsb_get_pattern": (C.c_int, [_H, C.c_int, c_int_p, c_int_p]),
     "nsb_set_halo": (C.c_int, [_H, C.c_int32, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "nsb_p2p_export": (C.c_int, [_H, C.c_void_p]),
+    "nsb_p2p_attach": (C.c_int, [_H, C.c_void_p]),
     "nsb_set_dirichlet": (C.c_int, [_H, C.c_int32, c_int_p]),
     "nsb_set_dirichlet_values": (C.c_int, [_H, c_double_p]),
     "nsb_set_neumann_rhs": (C.c_int, [_H, c_double_p]),

@@ -335,7 +335,10 @@ __device__ __forceinline__ double block_sum(double v)
   return s; // valid in thread 0
 }
 
-__device__ __forceinline__ void finish_reduce(double part, double *partials, unsigned *ticket, double *out)
+// ar.tab != nullptr (multi-rank, peer-memory transport): the last block also performs the all-reduce
+// over the ranks -- it stores the local sum into every peer's mailbox slot over NVLink, waits for the
+// peers and adds the partials in rank order (ar_exchange_block, nsb_internal.hpp).
+__device__ __forceinline__ void finish_reduce(double part, double *partials, unsigned *ticket, double *out, ArArgs ar)
 {
   __shared__ bool last;
   if (threadIdx.x == 0) {
@@ -349,7 +352,8 @@ __device__ __forceinline__ void finish_reduce(double part, double *partials, uns
     double v = 0.0;
     // fixed order: thread t sums partials t, t+256, ...; then block tree
     for (int b = threadIdx.x; b < int(gridDim.x); b += blockDim.x) v += __ldcg(partials + b);
-    const double s = block_sum(v);
+    double s = block_sum(v);
+    if (ar.tab) s = ar_exchange_block(ar.tab, ar.parity, ar.seq, s, threadIdx.x, 1);
     if (threadIdx.x == 0) { *out = s; *ticket = 0u; }
   }
 }
@@ -358,7 +362,7 @@ __device__ __forceinline__ void finish_reduce(double part, double *partials, uns
 // do not depend on the previous one), which is what a bandwidth-bound 16-24 B/element stream needs
 // to cover the HBM latency at full occupancy; the summation order is fixed by (grid, block) only.
 __global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ x, const double *__restrict__ y,
-                                             double *partials, unsigned *ticket, double *out)
+                                             double *partials, unsigned *ticket, double *out, ArArgs ar)
 {
   double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
   const int stride = gridDim.x * blockDim.x;
@@ -370,13 +374,13 @@ __global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ x
   }
   for (; i < n; i += stride) v0 += x[i] * y[i];
   const double s = block_sum((v0 + v1) + (v2 + v3));
-  finish_reduce(s, partials, ticket, out);
+  finish_reduce(s, partials, ticket, out, ar);
 }
 
 __global__ void __launch_bounds__(256) k_add_and_dot(int n, double *vv, const double *__restrict__ a,
                                                      double sign, const double *__restrict__ vp,
                                                      const double *vn, double *partials,
-                                                     unsigned *ticket, double *out)
+                                                     unsigned *ticket, double *out, ArArgs ar)
 {
   const double aa = sign * (*a);
   const bool self = (vn == vv);
@@ -399,26 +403,26 @@ __global__ void __launch_bounds__(256) k_add_and_dot(int n, double *vv, const do
     v0 += t * o;
   }
   const double s = block_sum((v0 + v1) + (v2 + v3));
-  finish_reduce(s, partials, ticket, out);
+  finish_reduce(s, partials, ticket, out, ar);
 }
 
 static inline unsigned rgrid(int n) { return unsigned(std::max(1, std::min((n + 255) / 256, kRedBlocks))); }
 
-void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev)
+void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev, ArArgs ar)
 {
   double *partials = H.d_scratch.p + 64;
   unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024);
-  k_dot<<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), x, y, partials, ticket, out_dev);
+  k_dot<<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), x, y, partials, ticket, out_dev, ar);
   H.launches++;
 }
 
 void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
-                         const double *v_next, double *out_dev)
+                         const double *v_next, double *out_dev, ArArgs ar)
 {
   double *partials = H.d_scratch.p + 64;
   unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024);
   k_add_and_dot<<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), vv, a_dev, sign, v_prev, v_next, partials, ticket,
-                                                out_dev);
+                                                out_dev, ar);
   H.launches++;
 }
 
@@ -431,7 +435,7 @@ constexpr int kMdBlocks = 592; // 148 * 4: NV + 1 independent loads per thread a
 template <int NV>
 __global__ void __launch_bounds__(256) k_multi_dot(int n, const double *__restrict__ vv, const double *__restrict__ V,
                                                    size_t ld, int with_self, double *partials, unsigned *ticket,
-                                                   double *out, double *out_self)
+                                                   double *out, double *out_self, ArArgs ar)
 {
   double acc[NV + 1];
 #pragma unroll
@@ -454,13 +458,20 @@ __global__ void __launch_bounds__(256) k_multi_dot(int n, const double *__restri
   }
   __syncthreads();
   if (!last) return;
+  __shared__ double fin[NV + 1];
   for (int j = 0; j <= NV; ++j) {
-    if (j == NV && !with_self) break;
     double v = 0.0;
     for (int b = threadIdx.x; b < int(gridDim.x); b += blockDim.x) v += __ldcg(partials + j * kMdBlocks + b);
     const double s = block_sum(v);
-    if (threadIdx.x == 0) { if (j < NV) out[j] = s; else *out_self = s; }
+    if (threadIdx.x == 0) fin[j] = s;
   }
+  __syncthreads();
+  const int j = threadIdx.x;
+  double s = j <= NV ? fin[j] : 0.0;
+  // all NV + 1 values cross the ranks in ONE exchange by the same block that finished the reduction
+  if (ar.tab) s = ar_exchange_block(ar.tab, ar.parity, ar.seq, s, j, NV + 1);
+  if (j < NV) out[j] = s;
+  else if (j == NV && with_self) *out_self = s;
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
@@ -468,7 +479,7 @@ __global__ void __launch_bounds__(256) k_multi_dot(int n, const double *__restri
 template <int NV>
 __global__ void __launch_bounds__(256) k_multi_axpy(int n, double *__restrict__ vv, const double *__restrict__ V,
                                                     size_t ld, const double *__restrict__ h, int with_norm,
-                                                    double *partials, unsigned *ticket, double *out_norm2)
+                                                    double *partials, unsigned *ticket, double *out_norm2, ArArgs ar)
 {
   double hh[NV];
 #pragma unroll
@@ -483,67 +494,69 @@ __global__ void __launch_bounds__(256) k_multi_axpy(int n, double *__restrict__ 
   }
   if (!with_norm) return;
   const double s = block_sum(acc);
-  finish_reduce(s, partials, ticket, out_norm2);
+  finish_reduce(s, partials, ticket, out_norm2, ar);
 }
 
 template <int NV>
 static void multi_dot_t(Handle &H, int n, const double *vv, const double *V, size_t ld, bool with_self, double *out,
-                        double *out_self)
+                        double *out_self, ArArgs ar)
 {
   double *partials = H.d_scratch.p + 64 + 1024 + 8;
   unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024 + 8 + 9 * 1024);
   const unsigned grid = unsigned(std::max(1, std::min((n + 255) / 256, kMdBlocks)));
-  k_multi_dot<NV><<<grid, 256, 0, H.stream>>>(std::max(n, 0), vv, V, ld, with_self ? 1 : 0, partials, ticket, out, out_self);
+  k_multi_dot<NV><<<grid, 256, 0, H.stream>>>(std::max(n, 0), vv, V, ld, with_self ? 1 : 0, partials, ticket, out, out_self, ar);
   H.launches++;
 }
 template <int NV>
 static void multi_axpy_t(Handle &H, int n, double *vv, const double *V, size_t ld, const double *h, bool with_norm,
-                         double *out_norm2)
+                         double *out_norm2, ArArgs ar)
 {
   double *partials = H.d_scratch.p + 64;
   unsigned *ticket = reinterpret_cast<unsigned *>(H.d_scratch.p + 64 + 1024);
-  k_multi_axpy<NV><<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), vv, V, ld, h, with_norm ? 1 : 0, partials, ticket, out_norm2);
+  k_multi_axpy<NV><<<rgrid(n), 256, 0, H.stream>>>(std::max(n, 0), vv, V, ld, h, with_norm ? 1 : 0, partials, ticket, out_norm2, ar);
   H.launches++;
 }
 
 // h[j] = vv . V_j for j < nv (V_j = V + j*ld), *self = vv . vv; groups of 8 vectors per pass over vv
 void vec_multi_dot_dev(Handle &H, int n, const double *vv, const double *V, size_t ld, int nv, double *h_dev,
-                       double *self_dev)
+                       double *self_dev, bool allreduce)
 {
   for (int j0 = 0; j0 < nv; j0 += 8) {
     const int g = std::min(8, nv - j0);
     const bool self = (j0 == 0) && self_dev;
     const double *Vg = V + size_t(j0) * ld;
+    const ArArgs ar = allreduce ? halo_ar_args(H) : ArArgs{nullptr, 0, 0};
     switch (g) {
-      case 1: multi_dot_t<1>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 2: multi_dot_t<2>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 3: multi_dot_t<3>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 4: multi_dot_t<4>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 5: multi_dot_t<5>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 6: multi_dot_t<6>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      case 7: multi_dot_t<7>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
-      default: multi_dot_t<8>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev); break;
+      case 1: multi_dot_t<1>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 2: multi_dot_t<2>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 3: multi_dot_t<3>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 4: multi_dot_t<4>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 5: multi_dot_t<5>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 6: multi_dot_t<6>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      case 7: multi_dot_t<7>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
+      default: multi_dot_t<8>(H, n, vv, Vg, ld, self, h_dev + j0, self_dev, ar); break;
     }
   }
 }
 
 // vv -= sum_{j<nv} h[j] V_j ; *norm2_dev = |vv|^2 afterwards (computed by the last group)
 void vec_multi_axpy_dev(Handle &H, int n, double *vv, const double *V, size_t ld, int nv, const double *h_dev,
-                        double *norm2_dev)
+                        double *norm2_dev, bool allreduce)
 {
   for (int j0 = 0; j0 < nv; j0 += 8) {
     const int g = std::min(8, nv - j0);
     const bool nrm = (j0 + 8 >= nv) && norm2_dev;
     const double *Vg = V + size_t(j0) * ld;
+    const ArArgs ar = (allreduce && nrm) ? halo_ar_args(H) : ArArgs{nullptr, 0, 0};
     switch (g) {
-      case 1: multi_axpy_t<1>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 2: multi_axpy_t<2>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 3: multi_axpy_t<3>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 4: multi_axpy_t<4>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 5: multi_axpy_t<5>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 6: multi_axpy_t<6>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      case 7: multi_axpy_t<7>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
-      default: multi_axpy_t<8>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev); break;
+      case 1: multi_axpy_t<1>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 2: multi_axpy_t<2>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 3: multi_axpy_t<3>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 4: multi_axpy_t<4>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 5: multi_axpy_t<5>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 6: multi_axpy_t<6>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      case 7: multi_axpy_t<7>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
+      default: multi_axpy_t<8>(H, n, vv, Vg, ld, h_dev + j0, nrm, norm2_dev, ar); break;
     }
   }
 }

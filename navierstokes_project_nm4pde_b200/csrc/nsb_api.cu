@@ -392,6 +392,21 @@ extern "C" int nsb_check_pattern(nsb_handle h, int blk, const int32_t *rowptr, c
   });
 }
 
+extern "C" int nsb_p2p_export(nsb_handle h, void *handle64)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!handle64) throw ArgError("nsb_p2p_export: null output");
+    halo_p2p_export(H, handle64);
+  });
+}
+extern "C" int nsb_p2p_attach(nsb_handle h, const void *handles)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!handles) throw ArgError("nsb_p2p_attach: null handles");
+    halo_p2p_attach(H, handles);
+  });
+}
+
 extern "C" int nsb_set_halo(nsb_handle h, int32_t n_nb, const int32_t *nb_ranks, const int32_t *send_node_ptr,
                             const int32_t *send_node_idx, const int32_t *recv_node_cnt, const int32_t *send_p_ptr,
                             const int32_t *send_p_idx, const int32_t *recv_p_cnt)
@@ -769,6 +784,7 @@ extern "C" double nsb_stat(nsb_handle h, const char *name)
   if (n == "cnt_sync") return double(H.cnt_sync);
   if (n == "nnz_iluF") return double(H.iluF.nnz);
   if (n == "nnz_iluS") return double(H.iluS.nnz);
+  if (n == "p2p") return halo_is_p2p(H) ? 1.0 : 0.0;
   if (n == "levels_F_fwd") return double(H.iluF.lvl_ptr_f.size()) - 1;
   if (n == "levels_F_bwd") return double(H.iluF.lvl_ptr_b.size()) - 1;
   if (n == "levels_S_fwd") return double(H.iluS.lvl_ptr_f.size()) - 1;

@@ -136,6 +136,73 @@ struct DevIlu {
 
 struct Halo; // multi-rank exchange (halo.cu)
 
+// ---- peer-memory transport (halo.cu): mailbox layout shared by all ranks, and the device helpers the
+// fused reductions use
+constexpr int kMaxRanks = 16, kArSlots = 64;
+struct MailHdr {
+  long long dir_u[kMaxRanks], dir_p[kMaxRanks]; // where rank r's values go in this rank's inbox (-1: none)
+  long long nvals_u, nvals_p;                   // values per inbox buffer (one parity)
+  unsigned long long ar_flag[2][kMaxRanks];     // [parity][source rank] = sequence number of the last push
+  unsigned long long hu_flag[2][kMaxRanks];
+  unsigned long long hp_flag[2][kMaxRanks];
+  double ar_slot[2][kMaxRanks][kArSlots];
+};
+struct PeerTab {
+  int nranks, me, n_nb;
+  MailHdr *peer[kMaxRanks];                      // mapped mailboxes (peer[me] = own)
+  int nb_rank[kMaxRanks];
+  int send_ptr_u[kMaxRanks + 1], send_ptr_p[kMaxRanks + 1];
+  double *dst_u[kMaxRanks], *dst_p[kMaxRanks];   // parity-0 destination of my values in neighbour k's inbox
+  long long stride_u[kMaxRanks], stride_p[kMaxRanks];
+};
+struct ArArgs {
+  const PeerTab *tab; // nullptr: no fused all-reduce
+  int parity;
+  unsigned long long seq;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *f >= seq; a peer that never arrives traps the kernel (an error instead of a hang)
+__device__ __forceinline__ void wait_flag(const unsigned long long *f, unsigned long long seq)
+{
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < seq) {
+    __nanosleep(40);
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+// All-reduce (sum) of n <= kArSlots values held one per thread (thread j holds value j) of ONE block;
+// every thread of the block must call.  Stores the value into every peer's slot, raises the flags,
+// waits for all peers and adds the partials in rank order (bitwise identical on every rank).
+__device__ __forceinline__ double ar_exchange_block(const PeerTab *T, int parity, unsigned long long seq, double v, int j, int n)
+{
+  const int nr = T->nranks, me = T->me;
+  if (j < n)
+    for (int r = 0; r < nr; ++r) T->peer[r]->ar_slot[parity][me][j] = v;
+  __threadfence_system();
+  __syncthreads();
+  if (j < nr) {
+    st_release_sys(&T->peer[j]->ar_flag[parity][me], seq);
+    wait_flag(&T->peer[me]->ar_flag[parity][j], seq);
+  }
+  __syncthreads();
+  double s = 0.0;
+  if (j < n)
+    for (int r = 0; r < nr; ++r) s += __ldcg(&T->peer[me]->ar_slot[parity][r][j]);
+  return s;
+}
+#endif
+
 struct Handle {
   int dim = 0, n2 = 0, nv1 = 0, dpc = 0;
   int device = 0, nranks = 1, rank = 0;
@@ -249,15 +316,16 @@ void vec_scale_inv_dev(Handle &H, int n, const double *s_dev, double *x);       
 void vec_pointwise(Handle &H, int n, const double *d, double *x);                  // x *= d
 void vec_pointwise_out(Handle &H, int n, const double *d, const double *x, double *y); // y = d .* x
 // out_dev[0] = sum x_i y_i over n entries (this rank); deterministic two-stage reduction
-void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev);
+void vec_dot_dev(Handle &H, int n, const double *x, const double *y, double *out_dev, ArArgs ar = ArArgs{nullptr, 0, 0});
 // vv += sign * (*a_dev) * v_prev ; out_dev = vv . v_next      (SolverGMRES add_and_dot)
 void vec_add_and_dot_dev(Handle &H, int n, double *vv, const double *a_dev, double sign, const double *v_prev,
-                         const double *v_next, double *out_dev);
+                         const double *v_next, double *out_dev, ArArgs ar = ArArgs{nullptr, 0, 0});
 // batched classical Gram-Schmidt pieces: h[j] = vv . V_j (j < nv), *self = vv . vv ; vv -= sum h[j] V_j
+// allreduce = true (multi-rank, peer-memory transport only): the kernels also sum over the ranks
 void vec_multi_dot_dev(Handle &H, int n, const double *vv, const double *V, size_t ld, int nv, double *h_dev,
-                       double *self_dev);
+                       double *self_dev, bool allreduce = false);
 void vec_multi_axpy_dev(Handle &H, int n, double *vv, const double *V, size_t ld, int nv, const double *h_dev,
-                        double *norm2_dev);
+                        double *norm2_dev, bool allreduce = false);
 void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering);
 void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val);
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y); // y = U^-1 D^-1 L^-1 x
@@ -304,5 +372,9 @@ void halo_set_plan(Handle &H, int n_nb, const int *nb_rank, const int *send_node
 void halo_exchange_u(Handle &H, double *x_u, int goff_u);
 void halo_exchange_p(Handle &H, double *x_p, int goff_p);
 void halo_allreduce(Handle &H, double *dev, int n);
+void halo_p2p_export(Handle &H, void *handle64);
+void halo_p2p_attach(Handle &H, const void *handles);
+bool halo_is_p2p(const Handle &H);
+ArArgs halo_ar_args(Handle &H);
 
 } // namespace nsb

@@ -52,15 +52,17 @@ void reduce_fetch(Handle &H, double *dev, int n, double *host_out)
 // dot product over the owned entries, summed over ranks, result left on the device
 static void dot_dev(Handle &H, int n, const double *x, const double *y, double *out)
 {
-  vec_dot_dev(H, n, x, y, out);
   H.cnt_dot++;
+  if (halo_is_p2p(H)) { vec_dot_dev(H, n, x, y, out, halo_ar_args(H)); return; } // all-reduce inside the kernel
+  vec_dot_dev(H, n, x, y, out);
   if (H.nranks > 1) halo_allreduce(H, out, 1);
 }
 static void add_and_dot_dev(Handle &H, int n, double *vv, const double *a, double sign, const double *vp,
                             const double *vn, double *out)
 {
-  vec_add_and_dot_dev(H, n, vv, a, sign, vp, vn, out);
   H.cnt_dot++;
+  if (halo_is_p2p(H)) { vec_add_and_dot_dev(H, n, vv, a, sign, vp, vn, out, halo_ar_args(H)); return; }
+  vec_add_and_dot_dev(H, n, vv, a, sign, vp, vn, out);
   if (H.nranks > 1) halo_allreduce(H, out, 1);
 }
 static double norm_host(Handle &H, int n, const double *x, double *slot)
@@ -150,13 +152,14 @@ static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, in
         // batched classical Gram-Schmidt: hd[0..dim-1] = V^T vv and hd[dim] = |vv|^2 from one fused
         // multi-dot (one all-reduce), vv -= V hd with the new |vv|^2 in hd[dim+1] (one all-reduce)
         double *hd = scal, *hd2 = scal + 32;
-        vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd, hd + dim);
+        const bool fused = halo_is_p2p(H); // peer-memory transport: the reductions all-reduce themselves
+        vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd, hd + dim, fused);
         H.cnt_dot++;
-        if (H.nranks > 1) halo_allreduce(H, hd, dim + 1);
-        vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd, orth == 2 ? nullptr : hd + dim + 1);
+        if (H.nranks > 1 && !fused) halo_allreduce(H, hd, dim + 1);
+        vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd, orth == 2 ? nullptr : hd + dim + 1, fused);
         bool second = (orth == 2);
         if (!second) {
-          if (H.nranks > 1) halo_allreduce(H, hd + dim + 1, 1);
+          if (H.nranks > 1 && !fused) halo_allreduce(H, hd + dim + 1, 1);
           reduce_fetch(H, hd, dim + 2, hh.data());
           for (int i = 0; i < dim; ++i) h[i] = hh[i];
           // deal.II's test (solver_gmres.h, modified_gram_schmidt) on every vector
@@ -164,11 +167,11 @@ static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, in
         }
         double s2 = hh[dim + 1];
         if (second) {
-          vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, nullptr);
+          vec_multi_dot_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, nullptr, fused);
           H.cnt_dot++;
-          if (H.nranks > 1) halo_allreduce(H, hd2, dim);
-          vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, hd2 + dim);
-          if (H.nranks > 1) halo_allreduce(H, hd2 + dim, 1);
+          if (H.nranks > 1 && !fused) halo_allreduce(H, hd2, dim);
+          vec_multi_axpy_dev(H, n, vv, V, size_t(sp.ld), dim, hd2, hd2 + dim, fused);
+          if (H.nranks > 1 && !fused) halo_allreduce(H, hd2 + dim, 1);
           if (orth == 2) {
             reduce_fetch(H, scal, 64, hh.data());
             for (int i = 0; i < dim; ++i) h[i] = hh[i] + hh[32 + i];

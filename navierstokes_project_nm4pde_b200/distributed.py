@@ -151,6 +151,7 @@ class DistributedNavierStokes(NavierStokes):
         e.set_params(deltat=self.deltat, **self.param_overrides)
         e.set_halo(*halo_arrays(loc, send_nodes, send_p))
         e.finalize()
+        self.transport = self._enable_peer_memory(e)
         self.nu = e.params.nu
         # local view of the global Dirichlet list (ghost rows included: their B^T rows are cleared too)
         lnode = loc["g2l_node"][self._dir_nodes]
@@ -166,6 +167,39 @@ class DistributedNavierStokes(NavierStokes):
         # local sizes in the caller layout [u (owned, ghost) | p (owned, ghost)]
         self.n_u, self.n_p, self.N = dim * nn, npl, dim * nn + npl
         return self
+
+    def _enable_peer_memory(self, e):
+        """Map every rank's mailbox into every other rank (CUDA IPC over NVLink) so that ghost exchange
+        and all-reduce become direct stores into peer HBM (csrc/halo.cu).  NSB_P2P=0 keeps NCCL; a box
+        without peer mapping falls back to NCCL on every rank (the decision is made collectively)."""
+        import os
+        import sys
+
+        import torch.distributed as dist
+
+        if os.environ.get("NSB_P2P", "1") == "0" or dist.get_backend() != "nccl":
+            return "nccl"
+        try:
+            mine = e.p2p_export()
+        except Exception as ex:  # noqa: BLE001
+            mine = None
+            print(f"[rank {self.rank}] peer-memory export failed: {ex}", file=sys.stderr)
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, mine)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                e.p2p_attach(handles)
+            except Exception as ex:  # noqa: BLE001
+                ok = False
+                print(f"[rank {self.rank}] peer-memory attach failed: {ex}", file=sys.stderr)
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            if ok:
+                raise RuntimeError("peer-memory transport came up on some ranks only")
+            return "nccl"
+        return "p2p"
 
     def initial_condition(self):
         if self.variant != "conv":

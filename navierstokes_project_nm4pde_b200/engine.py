@@ -253,6 +253,17 @@ class Engine:
         arrs = [a if a.size else np.zeros(1, np.int32) for a in arrs]
         self._ck(self.L.nsb_set_halo(self.h, len(nb_ranks), *[iptr(a) for a in arrs]))
 
+    def p2p_export(self):
+        """64-byte CUDA IPC handle of this rank's mailbox (after set_halo)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.nsb_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: the nranks 64-byte handles in rank order; switches the transport to peer memory."""
+        blob = b"".join(handles)
+        self._ck(self.L.nsb_p2p_attach(self.h, C.c_char_p(blob)))
+
     def pattern(self, blk):
         b = BLK[blk] if isinstance(blk, str) else blk
         nr, nnz = C.c_int32(0), C.c_int64(0)

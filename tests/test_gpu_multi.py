@@ -1,6 +1,6 @@
-"""N > 1 path on real GPUs (`-m gpu`, needs >= 2 devices): two ranks with NCCL halo exchange and
-all-reduced dot products must reproduce the oracle run with the same block-Jacobi partition
-(the reference's `mpirun -n 2` semantics)."""
+"""N > 1 path on real GPUs (`-m gpu`, needs >= 2 devices): two ranks -- ghost exchange and all-reduced
+dot products over peer memory (NVLink P2P stores, csrc/halo.cu) or over NCCL -- must reproduce the
+oracle run with the same block-Jacobi partition (the reference's `mpirun -n 2` semantics)."""
 import os
 import socket
 
@@ -18,8 +18,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case_name, ordering, out_q):
+def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
     import sys
+
+    os.environ["NSB_P2P"] = "1" if transport == "p2p" else "0"
 
     import torch
     import torch.distributed as dist
@@ -39,9 +41,11 @@ def _worker(rank, world, port, case_name, ordering, out_q):
         dist.broadcast_object_list(uid, src=0)
         case = T.Case(case_name)
         prob = DistributedNavierStokes(case.mesh, case.variant, T=1.0, deltat=case.dt, test_case=2 if case.dim == 3 else 3,
-                                       device=rank, nranks=world, rank=rank, unique_id=uid[0], ilu_ordering=ordering)
+                                       device=rank, nranks=world, rank=rank, unique_id=uid[0], ilu_ordering=ordering,
+                                       orthogonalisation=orth)
         prob.setup()
         e = prob.engine
+        assert prob.transport == transport and e.stat("p2p") == (1.0 if transport == "p2p" else 0.0), prob.transport
         e.set_solution(prob.initial_condition())
         its, sols = [], []
         t = 0.0
@@ -65,8 +69,11 @@ def _worker(rank, world, port, case_name, ordering, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case_name,ordering", [("cyl3d", 0), ("cyl3d", 1), ("cyl2d", 0), ("cube", 1)])
-def test_two_gpus_match_block_jacobi_oracle(case_name, ordering):
+@pytest.mark.parametrize("case_name,ordering,orth,transport",
+                         [("cyl3d", 0, 0, "p2p"), ("cyl3d", 1, 1, "p2p"), ("cyl2d", 0, 0, "p2p"), ("cube", 1, 0, "p2p"),
+                          ("cyl3d", 1, 1, "nccl"), ("cyl2d", 0, 0, "nccl")])
+def test_two_gpus_match_block_jacobi_oracle(case_name, ordering, orth, transport):
+    """ordering / orth: replay (0, 0) or throughput mode (multicolour ILU(0), batched Gram-Schmidt)."""
     from navierstokes_project_nm4pde_b200 import Engine
 
     if Engine.device_count() < 2:
@@ -78,10 +85,24 @@ def test_two_gpus_match_block_jacobi_oracle(case_name, ordering):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case_name, ordering, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case_name, ordering, orth, transport, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    import queue as _queue
+    import time as _time
+
+    res, deadline = [], _time.time() + 240
+    while len(res) < len(procs) and _time.time() < deadline:
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break  # a rank died: do not wait for the others (they would spin on its flags)
+    if len(res) < len(procs):
+        for p in procs:
+            p.kill()
+        pytest.fail(f"ranks did not finish: exit codes {[p.exitcode for p in procs]}")
+    res.sort(key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -91,6 +112,7 @@ def test_two_gpus_match_block_jacobi_oracle(case_name, ordering):
     part = np.concatenate([np.repeat(node_owner, dim), p_owner]).astype(np.int32)
     o = case.oracle()
     o.set_partition(part)
+    o.set_orthogonalisation(orth)
     if ordering == 1:
         # global ILU ordering = each rank's multicolour order of its owned block, rank after rank
         ou, op = [], []
