@@ -34,9 +34,12 @@ import numpy as np  # noqa: E402
 METRIC = "DoF-timesteps/sec (assemble_time_step + preconditioner init + outer GMRES)"
 UNIT = "DoF-timesteps/s"
 # workloads: name -> (s, nz) of HostMesh.cylinder3d; "cyl3d-20M" is BASELINE.json configs[4]
-WORKLOADS = {"cyl3d-20M": (8, 40), "cyl3d-16M": (8, 32), "cyl3d-2M": (4, 16), "cyl3d-270k": (2, 8),
+WORKLOADS = {"cyl3d-20M": (8, 40), "cyl3d-16M": (8, 32), "cyl3d-2M": (4, 16), "cyl3d-900k": (3, 12), "cyl3d-500k": (3, 7), "cyl3d-270k": (2, 8),
              "cyl3d-30k": (1, 3)}
-CPU_SAMPLE = "cyl3d-270k"  # bounded sample of the same mesh family for the CPU legs
+# Bounded sample of the same mesh family for the CPU legs.  DoF-timesteps/s falls with the mesh size
+# (outer iterations per step: ~25 at 0.27 M DoF, ~85 at 0.5 M, ~130 at 2 M, ~450 at 20 M), so the
+# sample is the largest mesh whose time step still costs ~30 s on 16 host cores.
+CPU_SAMPLE = "cyl3d-500k"
 DT = 2e-4                  # main3D.cpp:38
 
 
@@ -291,7 +294,7 @@ def run_gpu(args):
                            levels={k: e.stat(k) for k in ("levels_F_fwd", "levels_F_bwd", "levels_S_fwd",
                                                            "levels_S_bwd")}))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu(CPU_SAMPLE, 1, 0)
+        cpu = run_cpu(args.cpu_sample, 1, 0)
         out["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind="port",
                                    sample=cpu["sample"], seconds=cpu["seconds"])
     if rank == 0:
@@ -308,6 +311,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cyl3d-20M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default=CPU_SAMPLE, choices=sorted(WORKLOADS),
+                    help="mesh of the bounded CPU sample (cpu_baseline leg and --impl reference)")
     ap.add_argument("--ilu-ordering", type=int, default=1, choices=[0, 1],
                     help="0: natural row order (reference replay), 1: multicolour ILU(0) (throughput mode, default)")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
@@ -318,7 +323,7 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        cpu = run_cpu(CPU_SAMPLE, args.steps, args.warmup)
+        cpu = run_cpu(args.cpu_sample, args.steps, args.warmup)
         s, nz = WORKLOADS[args.workload]
         print(json.dumps(dict(
             impl="reference", metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
