@@ -270,8 +270,18 @@ def run_gpu(args):
         kern[name] = dict(ms=kms, bytes=kbytes, gbs=kbytes / (kms * 1e-3) / 1e9, calls_last_step=cnt,
                           share_last_step=cnt * kms / (1e3 * (t_prec[-1] + t_solve[-1]) + 1e-9))
     dom = max(kern, key=lambda k: kern[k]["share_last_step"])
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/r01_traffic.json; only valid for the workload / rank count it was captured on)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f).get(dom, {})
+        if tj.get("workload") == args.workload and world == 1:
+            traffic = tj.get("dram_bytes_per_apply", tj.get("dram_bytes_per_launch"))
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["gbs"], peak=peak, unit="GB/s",
-                    frac=kern[dom]["gbs"] / peak, traffic=None, peak_source=peak_src,
+                    frac=kern[dom]["gbs"] / peak, traffic=traffic, peak_source=peak_src,
                     kernels={k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                              for k, v in kern.items()})
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
