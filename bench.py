@@ -28,6 +28,14 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: keep NCCL's version banner off it
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
     os.environ["NCCL_DEBUG"] = "NONE"
+# torchrun exports OMP_NUM_THREADS=1 when it is unset, which would serialise the host side of setup()
+# (sparsity, scatter maps, ILU schedules: OpenMP in libnsb) on every rank and cripple the CPU arm.
+# Give every rank its share of the host cores instead (NSB_KEEP_OMP=1 keeps the caller's value).
+# Must happen before anything loads an OpenMP runtime.
+if os.environ.get("OMP_NUM_THREADS") == "1" and "WORLD_SIZE" in os.environ and not os.environ.get("NSB_KEEP_OMP"):
+    _world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"])))
+    _share = os.cpu_count() if "--impl" in sys.argv and "reference" in sys.argv else max(1, (os.cpu_count() or 1) // _world)
+    os.environ["OMP_NUM_THREADS"] = str(_share)
 
 import numpy as np  # noqa: E402
 
@@ -147,6 +155,15 @@ def run_cpu(workload, steps, warmup, threads=None):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (rank 0): where the wall time of a run goes; stdout stays one JSON line."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -160,8 +177,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     s, nz = WORKLOADS[args.workload]
+    log(f"process group up: world {world}, OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')}")
     t_setup = time.perf_counter()
     mesh = HostMesh.cylinder3d(s, nz)
+    log(f"mesh {args.workload}: {mesh.n_cells} cells")
     if world > 1:
         from navierstokes_project_nm4pde_b200.distributed import DistributedNavierStokes
 
@@ -181,6 +200,7 @@ def run_gpu(args):
     e = prob.engine
     n_dofs_global = prob.N_global if world > 1 else prob.N
     setup_s = time.perf_counter() - t_setup
+    log(f"setup done: {n_dofs_global} DoF, transport {getattr(prob, 'transport', 'none')}")
 
     def barrier():
         if world > 1:
@@ -216,9 +236,11 @@ def run_gpu(args):
         its_first, first_converged = args.first_step_cap, False
     e.set_params(outer_maxit=100000)  # NavierStokes3D.cpp:551
     barrier(); first_step_s = time.perf_counter() - t0
+    log(f"first step: {its_first} outer iterations, converged {first_converged}")
     for _ in range(args.warmup):
         tm += DT
-        e.assemble_step(tm); e.solve_step()
+        e.assemble_step(tm)
+        log(f"warm-up step: {e.solve_step()[0]} outer iterations")
 
     # ---- timed region 1: K steps, inputs resident in HBM (CUDA events on the launching stream)
     sampler = ClockSampler(local_rank)
@@ -235,6 +257,7 @@ def run_gpu(args):
         its.append(k); t_prec.append(tp); t_solve.append(ts)
     ms = e.timer_stop_ms()
     barrier()
+    log(f"timed steps: {its} outer iterations, {ms / args.steps:.0f} ms/step")
     launches = e.launch_count(reset=True)
     ms = reduce_max(ms)
     stats = {k: e.stat(k) for k in ("cnt_spmv_F", "cnt_spmv_S", "cnt_spmv_B", "cnt_spmv_Bt", "cnt_ilu_F", "cnt_ilu_S",
@@ -257,6 +280,7 @@ def run_gpu(args):
     barrier()
     ms_e2e = reduce_max(max(ms_e2e, (time.perf_counter() - t0) * 1e3))
     clocks = sampler.stop() if rank == 0 else None
+    log(f"e2e steps done: {ms_e2e / args.steps:.0f} ms/step")
     e2e = dict(value=n_dofs_global * args.steps / (ms_e2e * 1e-3), unit=UNIT,
                h2d_bytes_per_step=int(len(prob._dir_rows) * 8), d2h_bytes_per_step=int(prob.N * 8))
 

@@ -70,7 +70,7 @@ def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
 
 
 @pytest.mark.parametrize("case_name,ordering,orth,transport",
-                         [("cyl3d", 0, 0, "p2p"), ("cyl3d", 1, 1, "p2p"), ("cyl2d", 0, 0, "p2p"), ("cube", 1, 0, "p2p"),
+                         [("cyl3d", 0, 0, "p2p"), ("cyl3d", 1, 1, "p2p"), ("cyl2d", 0, 0, "p2p"), ("cube", 1, 0, "nccl"),
                           ("cyl3d", 1, 1, "nccl"), ("cyl2d", 0, 0, "nccl")])
 def test_two_gpus_match_block_jacobi_oracle(case_name, ordering, orth, transport):
     """ordering / orth: replay (0, 0) or throughput mode (multicolour ILU(0), batched Gram-Schmidt)."""
