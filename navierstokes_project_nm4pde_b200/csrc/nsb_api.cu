@@ -131,7 +131,11 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
   return guarded(h, [&](Handle &H) {
     if (!p) throw ArgError("nsb_set_params: null");
     if (p->precond_type < 0 || p->precond_type > 3) throw ArgError("Invalid preconditioner type");
-    if (p->gmres_tmp < 3 || p->gmres_tmp > 200) throw ArgError("nsb_set_params: gmres_tmp out of range");
+    // the device scalar slots of a Krylov solve are 64 doubles wide (solver.cu); the batched
+    // Gram-Schmidt splits them into two halves of 32
+    if (p->gmres_tmp < 3 || p->gmres_tmp > 60) throw ArgError("nsb_set_params: gmres_tmp must be in [3, 60]");
+    if (p->orthogonalisation == 1 && p->gmres_tmp > 30)
+      throw ArgError("nsb_set_params: orthogonalisation = 1 needs gmres_tmp <= 30 (the reference uses 30)");
     if (p->ilu_ordering < 0 || p->ilu_ordering > 1) throw ArgError("nsb_set_params: ilu_ordering must be 0 or 1");
     if (p->orthogonalisation < 0 || p->orthogonalisation > 1)
       throw ArgError("nsb_set_params: orthogonalisation must be 0 or 1");
