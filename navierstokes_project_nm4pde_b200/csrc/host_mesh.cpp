@@ -59,7 +59,11 @@ void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &c
       FaceRec r; r.v[2] = -1; r.cell = int(c); r.lf = f;
       int n = 0;
       for (int k = 0; k < nv1; ++k) if (k != f) r.v[n++] = cells[c * nv1 + k];
-      std::sort(r.v, r.v + dim);
+      if (r.v[0] > r.v[1]) std::swap(r.v[0], r.v[1]); // sort the dim (2 | 3) face vertices
+      if (dim == 3) {
+        if (r.v[1] > r.v[2]) std::swap(r.v[1], r.v[2]);
+        if (r.v[0] > r.v[1]) std::swap(r.v[0], r.v[1]);
+      }
       faces.push_back(r);
     }
   std::vector<size_t> order(faces.size());

@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10)) assemble_step_q_ke
 template <int DIM>
 __global__ void __launch_bounds__(32 * ((DIM == 2) ? 6 : 10), 3) assemble_step_t_kernel(AsmArgs a, int n_groups)
 {
-  constexpr int N2 = (DIM == 2) ? 6 : 10, NV1 = DIM + 1;
+  constexpr int N2 = (DIM == 2) ? 6 : 10;
   extern __shared__ __align__(16) double smem[];
-  // layout: T[i][a][k][j] (N2*N2*DIM*N2) | Mh[N2][N2] | sU[N2][DIM][32] | sUt[N2][DIM][32] | sX[NV1*DIM][32]
+  // layout: T[i][a][k][j] (N2*N2*DIM*N2) | Mh[N2][N2] | sU[N2][DIM][32] | sUt[N2][DIM][32] | sX[(DIM+1)*DIM][32]
   double *sT = smem;
   double *sMh = sT + N2 * N2 * DIM * N2;
   double(*sU)[DIM][32] = reinterpret_cast<double(*)[DIM][32]>(sMh + N2 * N2);

@@ -27,8 +27,8 @@ constexpr int kSM = 148;
 
 __device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c)
 {
-  double d;
-  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  // the fourth double of the padded node is loaded into a scratch PTX register and dropped
+  asm("{ .reg .f64 pad; ld.global.v4.f64 {%0,%1,%2,pad}, [%3]; }" : "=d"(a), "=d"(b), "=d"(c) : "l"(p));
 }
 
 // in / out vectors of a captured triangular solve: the graph bakes kernel arguments, so the

@@ -210,8 +210,6 @@ static int gmres(Handle &H, Space &sp, double *x, const double *b, double *V, in
         else re_orth = true;
       }
       if (!done && re_orth) {
-        double *ht = scal + n_tmp + 2; // not used: second pass reuses hd after the fetch
-        (void)ht;
         dot_dev(H, n, vv, V, hd);
         for (int i = 1; i < dim; ++i)
           add_and_dot_dev(H, n, vv, hd + i - 1, -1.0, V + size_t(i - 1) * sp.ld, V + size_t(i) * sp.ld, hd + i);
