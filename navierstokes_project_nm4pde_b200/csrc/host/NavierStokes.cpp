@@ -432,6 +432,18 @@ std::vector<double> NavierStokes::compute_forces()
   return {c_d, c_l};
 }
 
+// NavierStokes2D.cpp:862-936: pressure at A = (0.45, 0.2[, 0.205]) minus pressure at E = (0.55, 0.2[, 0.205])
+// through VectorTools::point_value; a point outside the mesh contributes 0 as in the reference.
+void NavierStokes::compute_pressure_difference()
+{
+  const double pa[3] = {0.45, 0.2, 0.205}, pe[3] = {0.55, 0.2, 0.205};
+  double va[4], ve[4];
+  const double p1 = nsh_dofs_point_value(dofs, solution.data(), pa, va) == 0 ? va[dim] : 0.0;
+  const double p2 = nsh_dofs_point_value(dofs, solution.data(), pe, ve) == 0 ? ve[dim] : 0.0;
+  pressure_difference = p1 - p2;
+  if (verbose) std::cout << "Pressure difference (P(A) - P(B)) = " << pressure_difference << std::endl;
+}
+
 // NavierStokes::solve (NavierStokes2D.cpp:699-750, NavierStokes3D.cpp:694-742, Convergence3D.cpp:724-764)
 void NavierStokes::solve()
 {
@@ -453,6 +465,7 @@ void NavierStokes::solve()
     if (time == deltat) assemble(time);
     else assemble_time_step(time);
     solve_time_step(time);
+    if (variant != Variant::Convergence3D && time == T - deltat) compute_pressure_difference(); // NavierStokes2D.cpp:735
     const bool forces = variant == Variant::Cylinder2D || (variant == Variant::Cylinder3D && time > forces_after);
     if (forces) {
       const std::vector<double> c = compute_forces();

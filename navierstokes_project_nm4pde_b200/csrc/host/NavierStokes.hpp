@@ -39,6 +39,7 @@ public:
   std::vector<double> time_prec, time_solve;
   std::vector<int> gmres_iterations;
   std::vector<std::array<double, 2>> coefficients_history; // (c_d, c_l) of every step that computed forces
+  double pressure_difference = 0.0;                        // P(A) - P(B) of the last compute_pressure_difference()
 
   // knobs the reference hard-codes; the drivers override them from the environment
   int max_steps = -1;        // stop after this many steps (reference: run to T)
@@ -55,6 +56,7 @@ protected:
   void assemble_time_step(const double &time); // NavierStokes2D.cpp:361-527
   void solve_time_step(double time);           // NavierStokes2D.cpp:530-639
   std::vector<double> compute_forces();        // NavierStokes2D.cpp:752-859 / NavierStokes3D.cpp:744-840
+  void compute_pressure_difference();          // NavierStokes2D.cpp:862-936 / NavierStokes3D.cpp:843-923
   void dirichlet_values(double time, std::vector<double> &vals) const;
   void neumann_rhs(double time, std::vector<double> &rhs) const; // Convergence3D.cpp:309-330
   void initial_condition(std::vector<double> &x) const;          // NavierStokes2D.cpp:708

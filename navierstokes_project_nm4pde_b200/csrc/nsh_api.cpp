@@ -121,6 +121,63 @@ int32_t nsh_dofs_boundary_faces(nsh_dofs d, nsh_mesh m, int32_t id, int32_t *fac
   return n;
 }
 
+// VectorTools::point_value of the (P2^dim, P1) solution at x: finds the cell containing x (first cell
+// whose barycentric coordinates are all >= -1e-10) and evaluates the dim velocity components and the
+// pressure there.  out[dim + 1]; returns 0, or NSB_ERR_ARG when no cell contains the point
+// (deal.II: ExcPointNotAvailableHere).
+int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out)
+{
+  if (!d || !solution || !x || !out) return NSB_ERR_ARG;
+  const nsb::Dofs &D = d->D;
+  const int dim = D.dim, nv1 = D.nv1, n2 = D.n2;
+  const int64_t n_u = int64_t(dim) * D.n_nodes;
+  for (int64_t c = 0; c < D.nc; ++c) {
+    const double *X = &D.cell_coords[size_t(c) * nv1 * dim];
+    // solve J lam' = x - x0 for the barycentric coordinates lam_1..lam_dim
+    double J[3][3], b[3], lam[4];
+    for (int r = 0; r < dim; ++r) {
+      b[r] = x[r] - X[r];
+      for (int k = 0; k < dim; ++k) J[r][k] = X[(k + 1) * dim + r] - X[r];
+    }
+    if (dim == 2) {
+      const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      lam[1] = (b[0] * J[1][1] - J[0][1] * b[1]) / det;
+      lam[2] = (J[0][0] * b[1] - b[0] * J[1][0]) / det;
+      lam[0] = 1.0 - lam[1] - lam[2];
+    } else {
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                   c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      // Cramer's rule, column by column
+      auto det3 = [](const double a[3], const double bb[3], const double cc[3]) {
+        return a[0] * (bb[1] * cc[2] - bb[2] * cc[1]) - bb[0] * (a[1] * cc[2] - a[2] * cc[1]) + cc[0] * (a[1] * bb[2] - a[2] * bb[1]);
+      };
+      const double c0[3] = {J[0][0], J[1][0], J[2][0]}, c1[3] = {J[0][1], J[1][1], J[2][1]}, c2[3] = {J[0][2], J[1][2], J[2][2]};
+      lam[1] = det3(b, c1, c2) / det;
+      lam[2] = det3(c0, b, c2) / det;
+      lam[3] = det3(c0, c1, b) / det;
+      lam[0] = 1.0 - lam[1] - lam[2] - lam[3];
+    }
+    bool inside = true;
+    for (int v = 0; v < nv1; ++v) inside &= (lam[v] >= -1e-10);
+    if (!inside) continue;
+    for (int k = 0; k <= dim; ++k) out[k] = 0.0;
+    const int *cn = &D.cell_nodes[size_t(c) * n2];
+    const int *cp = &D.cell_p[size_t(c) * nv1];
+    for (int v = 0; v < nv1; ++v) {
+      const double ph = lam[v] * (2.0 * lam[v] - 1.0);
+      for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[v] + k];
+      out[dim] += lam[v] * solution[n_u + cp[v]];
+    }
+    for (int e = 0; e < n2 - nv1; ++e) {
+      const double ph = 4.0 * lam[nsb::kEdgeA[e]] * lam[nsb::kEdgeB[e]];
+      for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[nv1 + e] + k];
+    }
+    return NSB_OK;
+  }
+  return NSB_ERR_ARG;
+}
+
 int nsh_partition_cells(nsh_mesh m, int nparts, int32_t *part)
 {
   if (!m || nparts < 1 || !part) return NSB_ERR_ARG;

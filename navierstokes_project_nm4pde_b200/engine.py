@@ -152,6 +152,14 @@ class HostDofs:
         self.L.nsh_dofs_boundary_nodes(self.h, self.mesh.h, iptr(ids), len(ids), iptr(out))
         return out[:n]
 
+    def point_value(self, solution, x):
+        """VectorTools::point_value: (u_0..u_{dim-1}, p) at x, or None when no cell contains x."""
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        xx = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(self.dim + 1)
+        rc = self.L.nsh_dofs_point_value(self.h, dptr(sol), dptr(xx), dptr(out))
+        return out if rc == 0 else None
+
     def boundary_faces(self, bid):
         n = self.L.nsh_dofs_boundary_faces(self.h, self.mesh.h, bid, None, None)
         fc, fl = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)

@@ -78,3 +78,26 @@ def test_dirichlet_lists_follow_the_reference_order():
     assert (v[~inlet] == 0).all() and (v[corner] == 0).all() and (v[inlet & ~corner, 0] > 0).all()
     assert (v[:, 1] == 0).all()
     assert len(np.unique(p._dir_rows)) == len(p._dir_rows)
+
+
+@pytest.mark.parametrize("gen,dim", [(lambda: HostMesh.cylinder2d(1), 2), (lambda: HostMesh.box(3, (3, 2, 2), (0, 0, 0), (1.0, 0.41, 0.41)), 3)])
+def test_point_value_reproduces_p2_p1_fields(gen, dim):
+    """VectorTools::point_value replacement (compute_pressure_difference, NavierStokes2D.cpp:862-936):
+    a quadratic velocity and a linear pressure are reproduced exactly anywhere inside the mesh; a
+    point outside (here: inside the cylinder hole / outside the box) is reported as not available."""
+    m = gen()
+    d = HostDofs(m)
+    X, P = d.node_xyz, d.p_xyz
+    quad = lambda x: 1.0 + x[..., 0] * x[..., 1] - 2.0 * x[..., 0] ** 2 + (x[..., -1] ** 2 if dim == 3 else 0.0)  # noqa: E731
+    lin = lambda x: 0.3 - 1.7 * x[..., 0] + 0.9 * x[..., 1] + (0.5 * x[..., -1] if dim == 3 else 0.0)  # noqa: E731
+    u = np.stack([(k + 1) * quad(X) for k in range(dim)], axis=1).ravel()
+    sol = np.concatenate([u, lin(P)])
+    pts = [[0.45, 0.2], [0.55, 0.2], [1.234, 0.111]] if dim == 2 else [[0.45, 0.2, 0.205], [0.9, 0.4, 0.01]]
+    for x in pts:
+        x = np.array(x)
+        v = d.point_value(sol, x)
+        assert v is not None
+        assert np.allclose(v[:dim], [(k + 1) * quad(x) for k in range(dim)], rtol=0, atol=1e-12)
+        assert abs(v[dim] - lin(x)) < 1e-12
+    outside = [0.2, 0.2] if dim == 2 else [1.5, 0.2, 0.2]
+    assert d.point_value(sol, np.array(outside)) is None
