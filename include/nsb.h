@@ -255,6 +255,9 @@ int32_t nsh_dofs_boundary_faces(nsh_dofs d, nsh_mesh m, int32_t id, int32_t *fac
 /* replaces: VectorTools::point_value (src/NavierStokes2D.cpp:875-889): velocity components and
  * pressure of the solution vector [u | p] at point x, out[dim + 1]; NSB_ERR_ARG when no cell holds x */
 int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out);
+/* minimal stand-in for DataOut::write_vtu (src/NavierStokes2D.cpp:642-675): ASCII .vtu, linear cells,
+ * point data "velocity" and "pressure" of the solution vector [u | p] */
+int nsh_write_vtu(nsh_mesh m, nsh_dofs d, const double *solution, const char *path);
 /* Partition cells into nparts (recursive coordinate bisection); part[n_cells]. */
 int nsh_partition_cells(nsh_mesh m, int nparts, int32_t *part);
 

@@ -6,10 +6,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <sys/stat.h>
 
 namespace {
 
@@ -353,6 +355,11 @@ void NavierStokes::solve_time_step(double)
     std::cout << "Time taken to solve Navier Stokes problem: " << ts << " seconds" << std::endl;
     std::cout << "Result:  " << its << " GMRES iterations" << std::endl;
   }
+  if (write_output && variant == Variant::Cylinder2D) { // gmres.csv: time, Re, iterations (NavierStokes2D.cpp:622-636)
+    const int Re = int(0.1 * 1.5 * std::sin(time_now * kPi / 8.0) / .001);
+    std::ofstream gm("gmres.csv", std::ios::app);
+    if (gm.is_open()) gm << time_now << ',' << Re << ',' << its << "\n";
+  }
   check(nsb_get_solution(engine, solution.data()), "nsb_get_solution"); // solution = solution_owned (:637)
 }
 
@@ -432,6 +439,25 @@ std::vector<double> NavierStokes::compute_forces()
   return {c_d, c_l};
 }
 
+// NavierStokes::output (NavierStokes2D.cpp:642-695, NavierStokes3D.cpp:643-692): one .vtu per call in
+// ./output2D_1/ (2D) or ./outputConvergence/ (3D and CONV, as the reference), and in 2D the
+// coefficients appended to coeff_2.csv.
+void NavierStokes::output(unsigned time_step, const std::vector<double> &coeff) const
+{
+  const std::string dir = variant == Variant::Cylinder2D ? "./output2D_1/" : "./outputConvergence/";
+  const std::string name = variant == Variant::Cylinder2D ? "output-navier-stokes-2D" : "output-navier-stokes-3D";
+  mkdir(dir.c_str(), 0755);
+  char num[16];
+  std::snprintf(num, sizeof(num), "%03u", time_step);
+  const std::string path = dir + name + "_" + num + ".vtu";
+  if (nsh_write_vtu(mesh, dofs, solution.data(), path.c_str()) != 0) throw std::runtime_error("cannot write " + path);
+  if (verbose) std::cout << "Output written to " << name << std::endl;
+  if (variant == Variant::Cylinder2D && coeff.size() >= 2) {
+    std::ofstream coeff_file("coeff_2.csv", std::ios::app); // append mode as the reference (:682)
+    if (coeff_file.is_open()) coeff_file << time_step << "," << coeff[0] << "," << coeff[1] << "\n";
+  }
+}
+
 // NavierStokes2D.cpp:862-936: pressure at A = (0.45, 0.2[, 0.205]) minus pressure at E = (0.55, 0.2[, 0.205])
 // through VectorTools::point_value; a point outside the mesh contributes 0 as in the reference.
 void NavierStokes::compute_pressure_difference()
@@ -450,6 +476,7 @@ void NavierStokes::solve()
   if (verbose) std::cout << "===============================================\nApplying the initial condition" << std::endl;
   initial_condition(solution);
   check(nsb_set_solution(engine, solution.data()), "nsb_set_solution");
+  if (write_output) output(0, {0.0, 0.0}); // the initial solution (:712)
   double c_D_max = -999, c_L_min = 999, time = 0;
   unsigned time_step = 0;
   std::vector<double> neu;
@@ -467,11 +494,14 @@ void NavierStokes::solve()
     solve_time_step(time);
     if (variant != Variant::Convergence3D && time == T - deltat) compute_pressure_difference(); // NavierStokes2D.cpp:735
     const bool forces = variant == Variant::Cylinder2D || (variant == Variant::Cylinder3D && time > forces_after);
+    std::vector<double> c = {0.0, 0.0};
     if (forces) {
-      const std::vector<double> c = compute_forces();
+      c = compute_forces();
       c_D_max = std::max(c_D_max, c[0]);
       c_L_min = std::min(c_L_min, c[1]);
     }
+    // VTU every step in 2D and CONV (:743, Convergence3D.cpp:761), every 20 steps in 3D (NavierStokes3D.cpp:734)
+    if (write_output && (variant != Variant::Cylinder3D || time_step % 20 == 0)) output(time_step, c);
     if (max_steps > 0 && int(time_step) >= max_steps) break;
   }
   if (verbose && variant != Variant::Convergence3D) {

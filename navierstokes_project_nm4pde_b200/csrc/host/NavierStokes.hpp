@@ -46,6 +46,7 @@ public:
   int ilu_ordering = 0;      // 0: reference replay, 1: multicolour throughput mode
   int device = 0;
   double forces_after = 0.1; // NavierStokes3D.cpp:728 computes forces only for time > 0.1
+  bool write_output = false; // VTU per step (2D) / every 20 steps (3D), gmres.csv, coeff_2.csv as the reference
   bool verbose = true;
 
   const std::vector<double> &get_solution() const { return solution; }
@@ -57,6 +58,7 @@ protected:
   void solve_time_step(double time);           // NavierStokes2D.cpp:530-639
   std::vector<double> compute_forces();        // NavierStokes2D.cpp:752-859 / NavierStokes3D.cpp:744-840
   void compute_pressure_difference();          // NavierStokes2D.cpp:862-936 / NavierStokes3D.cpp:843-923
+  void output(unsigned time_step, const std::vector<double> &coeff) const; // NavierStokes2D.cpp:642-695
   void dirichlet_values(double time, std::vector<double> &vals) const;
   void neumann_rhs(double time, std::vector<double> &rhs) const; // Convergence3D.cpp:309-330
   void initial_condition(std::vector<double> &x) const;          // NavierStokes2D.cpp:708

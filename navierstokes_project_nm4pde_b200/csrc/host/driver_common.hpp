@@ -3,6 +3,7 @@
 // reference lacks (every constant there is a compile-time literal):
 //   NSB_MAX_STEPS=<n>   stop after n time steps      NSB_T=<T>  final time
 //   NSB_ILU_ORDERING=1  multicolour ILU(0) (throughput mode)     NSB_DEVICE=<id>
+//   NSB_OUTPUT=1        write the reference's side outputs (.vtu, gmres.csv, coeff_2.csv); off by default
 #pragma once
 #include <chrono>
 #include <cstdlib>
@@ -35,6 +36,7 @@ inline void apply_env(NavierStokes &problem)
   problem.ilu_ordering = env_int("NSB_ILU_ORDERING", 0);
   problem.device = env_int("NSB_DEVICE", 0);
   problem.forces_after = env_double("NSB_FORCES_AFTER", 0.1);
+  problem.write_output = env_int("NSB_OUTPUT", 0) != 0;
 }
 
 inline int write_forces_csv(const std::string &output_filename, const NavierStokes &problem, double deltat)

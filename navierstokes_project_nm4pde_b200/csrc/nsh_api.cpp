@@ -1,4 +1,5 @@
 // nsh_api.cpp -- C ABI of the host prerequisites (mesh, DoF numbering, partition); no GPU needed.
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/nsb.h"
@@ -176,6 +177,52 @@ int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, do
     return NSB_OK;
   }
   return NSB_ERR_ARG;
+}
+
+// Minimal stand-in for DataOut::write_vtu (src/NavierStokes2D.cpp:642-675): one ASCII .vtu with the
+// linear simplices of the mesh and, per vertex, "velocity" (3 components) and "pressure".  The P2
+// edge values are not written (deal.II's build_patches() without subdivisions does the same).
+int nsh_write_vtu(nsh_mesh m, nsh_dofs d, const double *solution, const char *path)
+{
+  if (!m || !d || !solution || !path) return NSB_ERR_ARG;
+  const nsb::Mesh &M = m->M;
+  const nsb::Dofs &D = d->D;
+  const int dim = M.dim, nv1 = dim + 1;
+  const int64_t nv = M.n_vertices(), nc = M.n_cells(), n_u = int64_t(dim) * D.n_nodes;
+  // vertex v <-> pressure DoF / P2 vertex node: take them from the first cell that touches v
+  std::vector<int> node_of(nv, -1), p_of(nv, -1);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int k = 0; k < nv1; ++k) {
+      const int v = M.cells[c * nv1 + k];
+      node_of[v] = D.cell_nodes[size_t(c) * D.n2 + k];
+      p_of[v] = D.cell_p[size_t(c) * nv1 + k];
+    }
+  FILE *f = std::fopen(path, "w");
+  if (!f) return NSB_ERR_IO;
+  std::fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n");
+  std::fprintf(f, "<UnstructuredGrid>\n<Piece NumberOfPoints=\"%lld\" NumberOfCells=\"%lld\">\n", (long long)nv, (long long)nc);
+  std::fprintf(f, "<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+  for (int64_t v = 0; v < nv; ++v)
+    std::fprintf(f, "%.17g %.17g %.17g\n", M.verts[v * dim], M.verts[v * dim + 1], dim == 3 ? M.verts[v * dim + 2] : 0.0);
+  std::fprintf(f, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
+  for (int64_t c = 0; c < nc; ++c) {
+    for (int k = 0; k < nv1; ++k) std::fprintf(f, "%d ", M.cells[c * nv1 + k]);
+    std::fprintf(f, "\n");
+  }
+  std::fprintf(f, "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
+  for (int64_t c = 0; c < nc; ++c) std::fprintf(f, "%lld\n", (long long)(c + 1) * nv1);
+  std::fprintf(f, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+  for (int64_t c = 0; c < nc; ++c) std::fprintf(f, "%d\n", dim == 2 ? 5 : 10); // VTK_TRIANGLE / VTK_TETRA
+  std::fprintf(f, "</DataArray>\n</Cells>\n<PointData Vectors=\"velocity\" Scalars=\"pressure\">\n");
+  std::fprintf(f, "<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+  for (int64_t v = 0; v < nv; ++v) {
+    const double *u = solution + size_t(dim) * node_of[v];
+    std::fprintf(f, "%.17g %.17g %.17g\n", u[0], u[1], dim == 3 ? u[2] : 0.0);
+  }
+  std::fprintf(f, "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n");
+  for (int64_t v = 0; v < nv; ++v) std::fprintf(f, "%.17g\n", solution[n_u + p_of[v]]);
+  std::fprintf(f, "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+  return std::fclose(f) == 0 ? NSB_OK : NSB_ERR_IO;
 }
 
 int nsh_partition_cells(nsh_mesh m, int nparts, int32_t *part)

@@ -160,6 +160,13 @@ class HostDofs:
         rc = self.L.nsh_dofs_point_value(self.h, dptr(sol), dptr(xx), dptr(out))
         return out if rc == 0 else None
 
+    def write_vtu(self, solution, path):
+        """DataOut::write_vtu stand-in: linear cells, vertex values of velocity and pressure."""
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        rc = self.L.nsh_write_vtu(self.mesh.h, self.h, dptr(sol), str(path).encode())
+        if rc:
+            raise NsbError(rc, f"cannot write {path}")
+
     def boundary_faces(self, bid):
         n = self.L.nsh_dofs_boundary_faces(self.h, self.mesh.h, bid, None, None)
         fc, fl = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)

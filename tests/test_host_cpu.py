@@ -101,3 +101,23 @@ def test_point_value_reproduces_p2_p1_fields(gen, dim):
         assert abs(v[dim] - lin(x)) < 1e-12
     outside = [0.2, 0.2] if dim == 2 else [1.5, 0.2, 0.2]
     assert d.point_value(sol, np.array(outside)) is None
+
+
+def test_vtu_writer(tmp_path):
+    """DataOut::write_vtu stand-in: a well-formed UnstructuredGrid with the mesh's points / cells and
+    the vertex values of velocity and pressure."""
+    import xml.etree.ElementTree as ET
+
+    m = HostMesh.cylinder2d(1)
+    d = HostDofs(m)
+    sol = np.concatenate([np.tile([1.5, -0.5], d.n_nodes), 2.0 + d.p_xyz[:, 0]])
+    path = tmp_path / "output-navier-stokes-2D_001.vtu"
+    d.write_vtu(sol, path)
+    root = ET.parse(path).getroot()
+    piece = root.find("UnstructuredGrid/Piece")
+    assert int(piece.get("NumberOfPoints")) == m.n_vertices and int(piece.get("NumberOfCells")) == m.n_cells
+    arrays = {a.get("Name"): np.array(a.text.split(), float) for a in piece.iter("DataArray") if a.get("Name")}
+    assert np.array_equal(arrays["connectivity"].astype(int).reshape(-1, 3), m.cells)
+    assert np.allclose(arrays["velocity"].reshape(-1, 3), [1.5, -0.5, 0.0])
+    pts = np.array(piece.find("Points/DataArray").text.split(), float).reshape(-1, 3)
+    assert np.allclose(pts[:, :2], m.vertices) and np.allclose(arrays["pressure"], 2.0 + m.vertices[:, 0])
