@@ -121,3 +121,70 @@ def test_vtu_writer(tmp_path):
     assert np.allclose(arrays["velocity"].reshape(-1, 3), [1.5, -0.5, 0.0])
     pts = np.array(piece.find("Points/DataArray").text.split(), float).reshape(-1, 3)
     assert np.allclose(pts[:, :2], m.vertices) and np.allclose(arrays["pressure"], 2.0 + m.vertices[:, 0])
+
+
+MSH41 = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$Entities
+4 4 1 0
+1 0 0 0 0
+2 1 0 0 0
+3 1 1 0 0
+4 0 1 0 0
+1 0 0 0 1 0 0 1 0 2 1 -2
+2 1 0 0 1 1 0 1 1 2 2 -3
+3 0 1 0 1 1 0 1 2 2 3 -4
+4 0 0 0 0 1 0 1 3 2 4 -1
+1 0 0 0 1 1 0 1 9 4 1 2 3 4
+$EndEntities
+$Nodes
+1 4 1 4
+2 1 0 4
+1
+2
+3
+4
+0 0 0
+1 0 0
+1 1 0
+0 1 0
+$EndNodes
+$Elements
+5 6 1 6
+1 1 1 1
+1 1 2
+1 2 1 1
+2 2 3
+1 3 1 1
+3 3 4
+1 4 1 1
+4 4 1
+2 1 2 2
+5 1 2 3
+6 1 3 4
+$EndElements
+"""
+
+
+def test_msh_v41_reader_and_malformed_files(tmp_path):
+    """GridIn::read_msh accepts Gmsh 4.1 ASCII: physical ids of the curves arrive through $Entities.
+    Unreadable input is refused (NULL handle -> NsbError), never half-read."""
+    p = tmp_path / "square41.msh"
+    p.write_text(MSH41)
+    m = HostMesh.read_msh(str(p))
+    assert m.dim == 2 and m.n_cells == 2 and m.n_vertices == 4
+    ids = {tuple(sorted(f.tolist())): int(i) for f, i in zip(m.bfaces, m.bface_ids)}
+    assert ids == {(0, 1): 0, (1, 2): 1, (2, 3): 2, (0, 3): 3}
+    X = m.vertices[m.cells]
+    assert (np.linalg.det(np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))) > 0).all()
+    d = HostDofs(m)
+    assert (d.n_nodes, d.n_p, d.dpc) == (9, 4, 15)
+    for bad, text in (("empty.msh", ""), ("binary.msh", "$MeshFormat\n2.2 1 8\n$EndMeshFormat\n"),
+                      ("nocells.msh", "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n1\n1 0 0 0\n$EndNodes\n$Elements\n0\n$EndElements\n")):
+        q = tmp_path / bad
+        q.write_text(text)
+        with pytest.raises(_lib.NsbError):
+            HostMesh.read_msh(str(q))
+    with pytest.raises(_lib.NsbError):
+        HostMesh.read_msh(str(tmp_path / "does_not_exist.msh"))
