@@ -106,6 +106,7 @@ static const int EDGE_B[6] = {1, 2, 0, 3, 3, 3};
 
 static void bary(int dim, const double *x, double *l, double gl[4][3])
 {
+  if (dim > 3) dim = 3; /* simplices only: l has dim + 1 <= 4 entries */
   double s = 0;
   for (int d = 0; d < dim; ++d) s += x[d];
   l[0] = 1.0 - s;
