@@ -1,4 +1,4 @@
-"""Host logic of the N > 1 path, exercised with world_size 2 on the gloo backend (CPU only):
+"""Host logic of the N > 1 path, exercised with world_size 2 and 4 on the gloo backend (CPU only):
 partition, ownership, two-layer ghost cells, halo plan and a halo-exchange-driven SpMV that must
 reproduce the serial product."""
 import os
@@ -110,14 +110,14 @@ def _worker(rank, world, port, case_name, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case_name", ["cyl2d", "cyl3d"])
-def test_two_rank_partition_and_halo(case_name):
+@pytest.mark.parametrize("case_name,world", [("cyl2d", 2), ("cyl3d", 2), ("cyl3d", 4)])
+def test_partition_and_halo_over_gloo(case_name, world):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case_name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case_name, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
