@@ -252,6 +252,11 @@ int32_t nsh_dofs_boundary_nodes(nsh_dofs d, nsh_mesh m, const int32_t *ids, int3
 /* Face-quadrature data on boundary faces with the given id (for the Neumann term and the
  * drag/lift integrals): returns n_faces; arrays may be NULL to query. */
 int32_t nsh_dofs_boundary_faces(nsh_dofs d, nsh_mesh m, int32_t id, int32_t *face_cell, int32_t *face_local);
+/* replaces: the face loop of NavierStokes::compute_forces over the faces with `boundary_id`
+ * (src/NavierStokes2D.cpp:752-859: QGauss<1>(3), (nu grad u - p I) n; src/NavierStokes3D.cpp:744-840:
+ * QGaussSimplex<2>(3), tangential formula); out[0] = drag, out[1] = lift (unscaled integrals) */
+int nsh_boundary_forces(nsh_mesh m, nsh_dofs d, const double *solution, int32_t boundary_id, double nu, double rho,
+                        double *out);
 /* replaces: VectorTools::point_value (src/NavierStokes2D.cpp:875-889): velocity components and
  * pressure of the solution vector [u | p] at point x, out[dim + 1]; NSB_ERR_ARG when no cell holds x */
 int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out);

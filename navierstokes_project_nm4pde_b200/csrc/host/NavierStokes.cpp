@@ -2,6 +2,8 @@
 // Citations are relative to /root/reference/Navier-Stokes.
 #include "NavierStokes.hpp"
 
+#include "../fe_simplex.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -18,90 +20,11 @@ namespace {
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kEsA = kPi / 4.0, kEsB = kPi / 2.0, kEsNu = 1e-2; // Convergence3D.hpp:54-56
 
-// QGaussSimplex<dim>(3) as forwarded to Witherden-Vincent by deal.II >= 9.4 (7 / 14 points), and
-// QGauss<1>(3); same tables as navierstokes_project_nm4pde_b200/quadrature.py.
-struct Rule {
-  std::vector<double> xi, w;
-  int dim;
-  int size() const { return int(w.size()); }
-};
-
-Rule gauss_simplex(int dim)
-{
-  Rule r;
-  r.dim = dim;
-  auto add = [&](std::initializer_list<double> p, double w) {
-    for (double v : p) r.xi.push_back(v);
-    r.w.push_back(w);
-  };
-  if (dim == 1) {
-    const double g = std::sqrt(0.6);
-    add({0.5 - 0.5 * g}, 5.0 / 18.0); add({0.5}, 8.0 / 18.0); add({0.5 + 0.5 * g}, 5.0 / 18.0);
-  } else if (dim == 2) {
-    const double s = std::sqrt(15.0);
-    add({1.0 / 3.0, 1.0 / 3.0}, 0.1125);
-    for (int k = 0; k < 2; ++k) {
-      const double a = (k == 0 ? 6.0 - s : 6.0 + s) / 21.0, w = (k == 0 ? 155.0 - s : 155.0 + s) / 2400.0;
-      add({a, a}, w); add({1.0 - 2.0 * a, a}, w); add({a, 1.0 - 2.0 * a}, w);
-    }
-  } else {
-    const double A[2] = {0.31088591926330060980, 0.092735250310891226402};
-    const double W[2] = {0.11268792571801585080 / 6.0, 0.073493043116361949544 / 6.0};
-    for (int k = 0; k < 2; ++k) {
-      const double a = A[k], b = 1.0 - 3.0 * a;
-      add({a, a, a}, W[k]); add({b, a, a}, W[k]); add({a, b, a}, W[k]); add({a, a, b}, W[k]);
-    }
-    const double c = 0.045503704125649649492, d = 0.5 - c, w = 0.042546020777081466438 / 6.0;
-    add({c, c, d}, w); add({c, d, c}, w); add({d, c, c}, w); add({c, d, d}, w); add({d, c, d}, w); add({d, d, c}, w);
-  }
-  return r;
-}
-
-const int kEdges[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
-
-// P2 / P1 shape values and physical gradients at barycentric point `lam` of a simplex whose
-// barycentric gradients are gl[v][d].
-void shape_p2(int dim, const double *lam, const double gl[4][3], double *phi, double (*dphi)[3])
-{
-  const int nv = dim + 1, ne = dim == 2 ? 3 : 6;
-  for (int v = 0; v < nv; ++v) {
-    phi[v] = lam[v] * (2.0 * lam[v] - 1.0);
-    for (int d = 0; d < dim; ++d) dphi[v][d] = (4.0 * lam[v] - 1.0) * gl[v][d];
-  }
-  for (int e = 0; e < ne; ++e) {
-    const int a = kEdges[e][0], b = kEdges[e][1];
-    phi[nv + e] = 4.0 * lam[a] * lam[b];
-    for (int d = 0; d < dim; ++d) dphi[nv + e][d] = 4.0 * (lam[a] * gl[b][d] + lam[b] * gl[a][d]);
-  }
-}
-
-// barycentric gradients and |det J| of the affine simplex X[v][d]
-double bary_gradients(int dim, const double *X, double gl[4][3])
-{
-  double J[3][3] = {{0}}, Ji[3][3] = {{0}};
-  for (int r = 0; r < dim; ++r)
-    for (int k = 0; k < dim; ++k) J[r][k] = X[(k + 1) * dim + r] - X[r];
-  double det;
-  if (dim == 2) {
-    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
-  } else {
-    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
-                 c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
-    Ji[0][0] = c00 / det; Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
-    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-    Ji[1][0] = c01 / det; Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
-    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-    Ji[2][0] = c02 / det; Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
-    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
-  }
-  for (int d = 0; d < dim; ++d) {
-    gl[0][d] = 0.0;
-    for (int k = 0; k < dim; ++k) { gl[k + 1][d] = Ji[k][d]; gl[0][d] -= Ji[k][d]; }
-  }
-  return std::fabs(det);
-}
+using nsb::fe::Rule;
+using nsb::fe::gauss_simplex;
+using nsb::fe::shape_p2;
+using nsb::fe::bary_gradients;
+using nsb::fe::kEdges;
 
 // InletVelocity::vector_value (NavierStokes2D.hpp:26-44, NavierStokes3D.hpp:25-43)
 double inlet_ux(int dim, const double *x, double t, int test_case)
@@ -367,70 +290,9 @@ void NavierStokes::solve_time_step(double)
 // NavierStokes3D.cpp:744-840 (QGaussSimplex<2>(3), tangential formula).
 std::vector<double> NavierStokes::compute_forces()
 {
-  const Rule q = gauss_simplex(dim - 1);
-  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
-  const double *cc = nsh_dofs_cell_coords(dofs);
-  const int nv = dim + 1, n2 = dim == 2 ? 6 : 10;
-  double drag = 0.0, lift = 0.0;
-  for (size_t f = 0; f < obstacle_cells.size(); ++f) {
-    const int c = obstacle_cells[f], lf = obstacle_faces[f];
-    const double *X = cc + size_t(c) * nv * dim;
-    double gl[4][3];
-    bary_gradients(dim, X, gl);
-    // outward unit normal of the face opposite to vertex lf: -grad(lambda_lf) normalised
-    double nrm = 0.0, n_out[3] = {0, 0, 0};
-    for (int d = 0; d < dim; ++d) nrm += gl[lf][d] * gl[lf][d];
-    nrm = std::sqrt(nrm);
-    for (int d = 0; d < dim; ++d) n_out[d] = -gl[lf][d] / nrm;
-    int vs[3], k = 0;
-    for (int v = 0; v < nv; ++v)
-      if (v != lf) vs[k++] = v;
-    double meas; // |edge| in 2D, 2 * area in 3D (weights of the reference face sum to 1 resp. 1/2)
-    if (dim == 2) {
-      meas = std::hypot(X[vs[1] * 2] - X[vs[0] * 2], X[vs[1] * 2 + 1] - X[vs[0] * 2 + 1]);
-    } else {
-      double e1[3], e2[3];
-      for (int d = 0; d < 3; ++d) { e1[d] = X[vs[1] * 3 + d] - X[vs[0] * 3 + d]; e2[d] = X[vs[2] * 3 + d] - X[vs[0] * 3 + d]; }
-      const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-      meas = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-    }
-    // nodal values of this cell (FESystem order: per vertex [u.., p], then per edge [u..])
-    double U[10][3], P[4];
-    for (int v = 0; v < nv; ++v) {
-      for (int d = 0; d < dim; ++d) U[v][d] = solution[cd[size_t(c) * dpc + v * (dim + 1) + d]];
-      P[v] = solution[cd[size_t(c) * dpc + v * (dim + 1) + dim]];
-    }
-    for (int e = 0; e < n2 - nv; ++e)
-      for (int d = 0; d < dim; ++d) U[nv + e][d] = solution[cd[size_t(c) * dpc + nv * (dim + 1) + e * dim + d]];
-    for (int iq = 0; iq < q.size(); ++iq) {
-      double lam[4] = {0, 0, 0, 0};
-      if (dim == 2) { lam[vs[0]] = 1.0 - q.xi[iq]; lam[vs[1]] = q.xi[iq]; }
-      else { lam[vs[0]] = 1.0 - q.xi[2 * iq] - q.xi[2 * iq + 1]; lam[vs[1]] = q.xi[2 * iq]; lam[vs[2]] = q.xi[2 * iq + 1]; }
-      double phi[10], dphi[10][3];
-      shape_p2(dim, lam, gl, phi, dphi);
-      double G[3][3] = {{0}}, p = 0.0; // G[i][j] = d u_i / d x_j
-      for (int a = 0; a < n2; ++a)
-        for (int i = 0; i < dim; ++i)
-          for (int j = 0; j < dim; ++j) G[i][j] += U[a][i] * dphi[a][j];
-      for (int v = 0; v < nv; ++v) p += P[v] * lam[v];
-      const double jxw = q.w[iq] * meas;
-      double n[3] = {-n_out[0], -n_out[1], -n_out[2]}; // normal_vector = -fe_face_values.normal_vector(q)
-      if (dim == 2) {
-        double force[2];
-        for (int i = 0; i < 2; ++i) force[i] = (nu * (G[i][0] * n[0] + G[i][1] * n[1]) - p * n[i]) * jxw;
-        drag += force[0];
-        lift += force[1];
-      } else {
-        const double nx = n[0], ny = n[1];
-        const double t[3] = {ny, -nx, 0.0}, t2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-        double ngt = 0.0; // n * grad u * (t / |t|^2)
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) ngt += n[i] * G[i][j] * t[j] / t2;
-        drag += (rho * nu * ngt * ny - p * nx) * jxw;
-        lift -= (rho * nu * ngt * nx + p * ny) * jxw;
-      }
-    }
-  }
+  double fl[2];
+  check(nsh_boundary_forces(mesh, dofs, solution.data(), 3, nu, rho, fl), "nsh_boundary_forces");
+  const double drag = fl[0], lift = fl[1];
   const double mean_v = inlet_mean_velocity(dim, test_case, time_now), D = 0.1, H = 0.41;
   const double den = dim == 2 ? mean_v * mean_v * D : rho * mean_v * mean_v * D * H;
   const double c_d = 2.0 * drag / den, c_l = 2.0 * lift / den;

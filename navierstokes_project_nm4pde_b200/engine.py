@@ -160,6 +160,15 @@ class HostDofs:
         rc = self.L.nsh_dofs_point_value(self.h, dptr(sol), dptr(xx), dptr(out))
         return out if rc == 0 else None
 
+    def boundary_forces(self, solution, boundary_id, nu, rho=1.0):
+        """(drag, lift) face integrals of NavierStokes::compute_forces over the faces with boundary_id."""
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        out = np.zeros(2)
+        rc = self.L.nsh_boundary_forces(self.mesh.h, self.h, dptr(sol), boundary_id, float(nu), float(rho), dptr(out))
+        if rc:
+            raise NsbError(rc, "boundary_forces")
+        return out
+
     def write_vtu(self, solution, path):
         """DataOut::write_vtu stand-in: linear cells, vertex values of velocity and pressure."""
         sol = np.ascontiguousarray(solution, dtype=np.float64)

@@ -188,3 +188,50 @@ def test_msh_v41_reader_and_malformed_files(tmp_path):
             HostMesh.read_msh(str(q))
     with pytest.raises(_lib.NsbError):
         HostMesh.read_msh(str(tmp_path / "does_not_exist.msh"))
+
+
+def _hole_measure(m, dim):
+    """Area (2D) / volume (3D) enclosed by the boundary faces with id 3, by the divergence theorem."""
+    F = m.bfaces[m.bface_ids == 3]
+    X = m.vertices
+    if dim == 2:
+        c = X[F].mean(axis=(0, 1))
+        a = 0.0
+        for e in F:
+            p, q = X[e[0]] - c, X[e[1]] - c
+            a += 0.5 * abs(p[0] * q[1] - p[1] * q[0])
+        return a
+    # the obstacle is a right prism (polygon x [0, H]) whose caps lie on the channel walls, so id 3 only
+    # holds its lateral surface: the cones from the centroid to the lateral faces make up 2/3 of it
+    c = X[F].mean(axis=(0, 1))
+    v = 0.0
+    for t in F:
+        p, q, r = X[t[0]] - c, X[t[1]] - c, X[t[2]] - c
+        v += abs(np.dot(p, np.cross(q, r))) / 6.0
+    return 1.5 * v
+
+
+@pytest.mark.parametrize("gen,dim", [(lambda: HostMesh.cylinder2d(1), 2), (lambda: HostMesh.cylinder3d(1, 3), 3)])
+def test_boundary_forces_exact_for_linear_fields(gen, dim):
+    """compute_forces face integrals (NavierStokes2D.cpp:752-859, NavierStokes3D.cpp:744-840) on the
+    obstacle (id 3).  With the reference's n = -(outward normal of the fluid cell) the integral of
+    -p n over the closed obstacle surface is -grad(p) * |hole| for a linear pressure; a constant
+    velocity gradient contributes nu G (closed integral of n) = 0 in the 2D formula."""
+    m = gen()
+    d = HostDofs(m)
+    X, P = d.node_xyz, d.p_xyz
+    beta, gamma = 0.7, -1.3
+    p = 2.0 + beta * P[:, 0] + gamma * P[:, 1]
+    if dim == 3:  # the cylinder spans the whole channel in z: its end caps lie on the walls (id 2), not on id 3
+        u = np.zeros(d.n_u)
+    else:
+        u = np.stack([0.3 * X[:, 0] - 0.2 * X[:, 1], 0.5 * X[:, 0] + 0.1 * X[:, 1]], axis=1).ravel()
+    drag, lift = d.boundary_forces(np.concatenate([u, p]), 3, nu=1e-3)
+    hole = _hole_measure(m, dim)
+    assert hole > 0
+    if dim == 2:
+        assert abs(drag + beta * hole) < 1e-12 and abs(lift + gamma * hole) < 1e-12
+    else:
+        # side surface only: the closed-surface identity holds for the x and y components because the
+        # missing caps have normals along z
+        assert abs(drag + beta * hole) < 1e-10 and abs(lift + gamma * hole) < 1e-10
