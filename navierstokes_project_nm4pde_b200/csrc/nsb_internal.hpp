@@ -286,7 +286,8 @@ struct Handle {
   long n_inner_F = 0, n_inner_S = 0, n_F_solves = 0, n_S_solves = 0, n_vmult = 0;
   long cnt_spmv_F = 0, cnt_spmv_S = 0, cnt_spmv_B = 0, cnt_spmv_Bt = 0, cnt_ilu_F = 0, cnt_ilu_S = 0, cnt_dot = 0,
        cnt_sync = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+  double t_step_dev_ms = 0; // device time of the steps run through nsb_step_host since the last reset
   int last_outer = 0;
   double last_res = 0, t_assemble_ms = 0, t_prec_ms = 0, t_solve_ms = 0;
 

@@ -10,6 +10,7 @@
 // stopping on the preconditioned residual; CG in the g = Ax - b formulation).
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <functional>
 
 #include "nsb_internal.hpp"
@@ -326,6 +327,18 @@ static void apply_Bt(Handle &H, const double *x, int goff, double *y)
   spmv_Bt(H, x, goff, y);
 }
 
+
+// An inner SolverGMRES / SolverCG that hits maxiter (or NaN) throws SolverControl::NoConvergence out of
+// Preconditioner::vmult in the reference and aborts the step; same here (-> NSB_ERR_NOCONV).
+static void check_inner(int rc, const char *what, const Control &ctl)
+{
+  if (rc == 0) return;
+  char buf[200];
+  std::snprintf(buf, sizeof(buf), "SolverControl::NoConvergence: inner %s stopped at step %d with residual %.6e (tol %.6e)",
+                what, ctl.last_step, ctl.last_value, ctl.tol);
+  throw NoConvergence(buf);
+}
+
 static void inner_gmres_F(Handle &H, double *x, int goff_x, const double *b, double tol)
 {
   auto &w = *H.ws;
@@ -336,9 +349,10 @@ static void inner_gmres_F(Handle &H, double *x, int goff_x, const double *b, dou
   sp.A = [&H](const double *xx, int goff, double *y) { apply_F(H, xx, goff, y); };
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluF, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
-  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
+  const int rc = gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_F += ctl.last_step;
   H.n_F_solves++;
+  check_inner(rc, "GMRES on F", ctl);
 }
 static void inner_gmres_S(Handle &H, double *x, int goff_x, const double *b, double tol)
 {
@@ -350,9 +364,10 @@ static void inner_gmres_S(Handle &H, double *x, int goff_x, const double *b, dou
   sp.A = [&H](const double *xx, int goff, double *y) { apply_S(H, xx, goff, y); };
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluS, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
-  gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
+  const int rc = gmres(H, sp, x, b, w.V_inner.p, H.prm.gmres_tmp, w.scal.p + 64, ctl, H.prm.orthogonalisation ? 1 : 0);
   H.n_inner_S += ctl.last_step;
   H.n_S_solves++;
+  check_inner(rc, "GMRES on the Schur complement", ctl);
 }
 static void inner_cg_S(Handle &H, double *x, int goff_x, const double *b, double tol)
 {
@@ -364,9 +379,10 @@ static void inner_cg_S(Handle &H, double *x, int goff_x, const double *b, double
   sp.A = [&H](const double *xx, int goff, double *y) { apply_S(H, xx, goff, y); };
   sp.P = [&H](const double *r, double *z) { ilu_solve(H, H.iluS, r, z); };
   Control ctl{H.prm.inner_maxit, tol};
-  cg(H, sp, x, b, w.tp[3].p, w.tp[4].p, w.tp[5].p, w.scal.p + 128, ctl);
+  const int rc = cg(H, sp, x, b, w.tp[3].p, w.tp[4].p, w.tp[5].p, w.scal.p + 128, ctl);
   H.n_inner_S += ctl.last_step;
   H.n_S_solves++;
+  check_inner(rc, "CG on the Schur complement", ctl);
 }
 
 // --------------------------------------------------------------------------------------------
