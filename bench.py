@@ -394,8 +394,8 @@ def run_gpu(args):
                            start_up_iterations=its_prep, start_up_s=prep_s, warmup_iterations=warm_its,
                            warmup_s=[round(x, 2) for x in warm_s], setup_s=setup_s, t_prec_s=t_prec, t_solve_s=t_solve,
                            last_step_counts=stats, wall_ms_per_step=wall_ms / steps,
-                           levels={k: e.stat(k) for k in ("levels_F_fwd", "levels_F_bwd", "levels_S_fwd",
-                                                           "levels_S_bwd")}))
+                           levels={k: e.stat(k) for k in ("levels_F_fwd", "sweeps_F", "sweeps_S", "ilu_blocks_F",
+                                                           "ilu_blocks_S")}))
     left = budget - (time.perf_counter() - _T0)
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1

@@ -643,6 +643,92 @@ static void multicolour_order(int n, const Csr &A, int n_owned_cols, int chunk_r
   if (colour_ptr.size() == 1) colour_ptr.push_back(0);
 }
 
+
+// Block multicolour ordering (algebraic block multi-colouring, Iwashita et al.): the rows are aggregated
+// into blocks of kBlkRows spatially adjacent rows (greedy breadth-first aggregation over the matrix
+// graph, seeds in natural order; a block that runs out of frontier is topped up from the next seed), the
+// BLOCK graph is coloured greedily, and the ILU ordering is (block colour, block, position in the
+// block).  Blocks of one colour do not touch, so a colour is solved by one launch with one warp per
+// block; inside a block the rows are eliminated sequentially (a lane per row, values handed on by
+// shuffles, kernels_sell.cu).  Against point multicolouring this (a) keeps most couplings inside a
+// block or between neighbouring blocks, so a triangular sweep gathers each vector entry from HBM ~5
+// instead of ~14 times, and (b) is a much stronger ILU(0): inner iteration counts equal those of the
+// natural ordering (measured with the oracle, profiles/README.md).
+constexpr int kBlkRows = 32;
+static void block_multicolour_order(int n, const Csr &A, int n_owned_cols, std::vector<int> &order,
+                                    std::vector<int> &colour_ptr, std::vector<int> &blk_ptr,
+                                    std::vector<int> &colour_blk)
+{
+  const int nc_lim = std::min(n, n_owned_cols);
+  std::vector<int> blk_of(n, -1), seq;
+  seq.reserve(n);
+  std::vector<int> q;
+  int nb = 0, cur = 0;
+  for (int seed = 0; seed < n; ++seed) {
+    if (blk_of[seed] >= 0) continue;
+    q.clear();
+    q.push_back(seed);
+    blk_of[seed] = nb; seq.push_back(seed);
+    if (++cur == kBlkRows) { ++nb; cur = 0; continue; }
+    size_t head = 0;
+    bool full = false;
+    while (head < q.size() && !full) {
+      const int u = q[head++];
+      for (int k = A.rowptr[u]; k < A.rowptr[u + 1]; ++k) {
+        const int v = A.colind[k];
+        if (v >= nc_lim || blk_of[v] >= 0) continue;
+        blk_of[v] = nb; seq.push_back(v); q.push_back(v);
+        if (++cur == kBlkRows) { ++nb; cur = 0; full = true; break; }
+      }
+    }
+  }
+  if (cur > 0) ++nb;
+  // rows of each block in aggregation order
+  std::vector<int> bstart(nb + 1, 0);
+  for (int i = 0; i < n; ++i) bstart[blk_of[i] + 1]++;
+  for (int b = 0; b < nb; ++b) bstart[b + 1] += bstart[b];
+  // (seq lists the blocks one after the other already: block b = seq[bstart[b] .. bstart[b+1]) )
+  // greedy colouring of the block graph in block order
+  std::vector<int> bcol(nb, -1), mark;
+  int ncol = 0;
+  for (int b = 0; b < nb; ++b) {
+    mark.assign(ncol + 1, 0);
+    for (int t = bstart[b]; t < bstart[b + 1]; ++t) {
+      const int u = seq[t];
+      for (int k = A.rowptr[u]; k < A.rowptr[u + 1]; ++k) {
+        const int v = A.colind[k];
+        if (v >= nc_lim) continue;
+        const int bb = blk_of[v];
+        if (bb != b && bcol[bb] >= 0) mark[bcol[bb]] = 1;
+      }
+    }
+    int c = 0;
+    while (mark[c]) ++c;
+    bcol[b] = c;
+    if (c == ncol) ++ncol;
+  }
+  // factor order: colour by colour, blocks in index order, rows in aggregation order
+  std::vector<int> ccnt(ncol + 1, 0);
+  for (int b = 0; b < nb; ++b) ccnt[bcol[b] + 1]++;
+  for (int c = 0; c < ncol; ++c) ccnt[c + 1] += ccnt[c];
+  colour_blk.assign(ccnt.begin(), ccnt.end());
+  std::vector<int> slot(ccnt.begin(), ccnt.end() - 1), blocks(nb);
+  for (int b = 0; b < nb; ++b) blocks[slot[bcol[b]]++] = b;
+  order.clear();
+  order.reserve(n);
+  blk_ptr.assign(1, 0);
+  colour_ptr.assign(1, 0);
+  for (int c = 0; c < ncol; ++c) {
+    for (int k = ccnt[c]; k < ccnt[c + 1]; ++k) {
+      const int b = blocks[k];
+      for (int t = bstart[b]; t < bstart[b + 1]; ++t) order.push_back(seq[t]);
+      blk_ptr.push_back(int(order.size()));
+    }
+    colour_ptr.push_back(int(order.size()));
+  }
+  if (colour_ptr.size() == 1) colour_ptr.push_back(0);
+}
+
 // rows per chunk of the multicolour ordering: NSB_ILU_CHUNK (rows), default 0 = one chunk.  Measured
 // at 19.9 M DoF (profiles/README.md): chunks of 0.8 / 1.25 / 2.5 M nodes make the F_s apply SLOWER
 // (3.3 / 2.9 / 2.2 ms against 1.68 ms unchunked) -- the 5x more, 5x smaller sweeps are latency-bound
@@ -662,8 +748,9 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   ilu.n = n;
   ilu.bs_rhs = bs_rhs;
   ilu.h_order.clear();
-  std::vector<int> colour_ptr;
+  std::vector<int> colour_ptr, blk_ptr, colour_blk;
   if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu_chunk_rows(bs_rhs), ilu.h_order, colour_ptr);
+  else if (ordering == 2) block_multicolour_order(n, A, n_owned_cols, ilu.h_order, colour_ptr, blk_ptr, colour_blk);
   else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
   const std::vector<int> &order = ilu.h_order;
   std::vector<int> pos(n_owned_cols > n ? n_owned_cols : n, -1);
@@ -700,6 +787,19 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   ilu.dinv.alloc(n);
   std::vector<int> rows;
   ilu.stream = false;
+  ilu.bsell = false;
+  if (ordering == 2) {
+    // numeric factorisation: exact dependency levels of the permuted pattern (about colours x the
+    // longest chain inside a block, ~200 launches once per time step); triangular solves: one launch
+    // per block colour (bsell_trsv)
+    level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);
+    ilu.lvl_rows_f.upload(rows);
+    ilu.lvl_ptr_b.assign(1, 0);
+    ilu.colour_ptr = colour_ptr;
+    bsell_build(ilu, rowptr, colind, diagpos, blk_ptr, colour_blk);
+    ilu.bsell = true;
+    return;
+  }
   if (ordering == 1) {
     // colours are a valid (contiguous) schedule in both directions: a row of colour c only
     // couples with rows of other colours
@@ -799,7 +899,8 @@ void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val)
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());
-  if (ilu.sell) {
+  if (ilu.bsell) bsell_fill(H, ilu);
+  else if (ilu.sell) {
     sell_fill(H, ilu.sellL, ilu.val.p);
     sell_fill(H, ilu.sellU, ilu.val.p);
   } else if (ilu.stream) stream_split_factors(H, ilu);
@@ -979,12 +1080,15 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
   const int nvals = ilu.n * ilu.bs_rhs;
   cudaStream_t s = H.stream;
   if (!ilu.graph_f) {
-    if (ilu.sell) ilu.io.alloc(2);
-    NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * size_t(ilu.sell ? 4 * ilu.n : nvals)));
+    if (ilu.sell || ilu.bsell) ilu.io.alloc(2);
+    const size_t stage = ilu.sell ? size_t(4) * ilu.n : ilu.bsell ? size_t(bsell_stride(ilu.bs_rhs)) * ilu.n : size_t(nvals);
+    NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * stage));
+    NSB_CUDA(cudaMemsetAsync(ilu.graph_x, 0, sizeof(double) * stage, s));
     cudaGraph_t g;
     const int64_t before = H.launches;
     NSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    if (ilu.sell) sell_trsv(H, ilu, ilu.graph_x, s);
+    if (ilu.bsell) bsell_trsv(H, ilu, ilu.graph_x, s);
+    else if (ilu.sell) sell_trsv(H, ilu, ilu.graph_x, s);
     else if (ilu.stream) stream_trsv(H, ilu, ilu.graph_x, s);
     else if (ilu.bs_rhs == 1) trsv_levels<1>(H, ilu, ilu.graph_x, s);
     else if (ilu.bs_rhs == 2) trsv_levels<2>(H, ilu, ilu.graph_x, s);
@@ -994,7 +1098,7 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;
   }
-  if (ilu.sell) { // permutation in / out fused into the first forward and every backward launch
+  if (ilu.sell || ilu.bsell) { // permutation in / out fused into the first forward and every backward launch
     sell_set_io(H, ilu, x, y);
     NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
     H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1);

@@ -295,6 +295,311 @@ void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
   NSB_CUDA(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Block multicolour triangular solves (ilu_ordering = 2; the ordering is built in kernels_linalg.cu:
+// block_multicolour_order).  One warp solves one block of <= 32 consecutive factor rows, one launch
+// sweeps all blocks of one block colour.  Per block:
+//   1. the entries coupling with OTHER blocks (final when this colour is swept) are streamed perfectly
+//      coalesced (packed, no ELL padding: P2 vertex nodes have 3x the row length of edge nodes), each
+//      lane multiplies one entry with the gathered node (one 256-bit load for 3 components), and a
+//      segmented warp scan keyed by the local row sums the products per row (fixed order:
+//      deterministic) into a per-warp accumulator in shared memory;
+//   2. the entries INSIDE the block are eliminated sequentially: lane l owns row l; at step r the
+//      finished value of row r is broadcast by shuffle and the lanes whose next entry sits in column r
+//      consume it (entries staged in shared memory, sorted by column, so a lane only advances a cursor).
+// The permutation into factor order is fused into the forward sweep (reads the caller's x through
+// `order`) and the inverse permutation into the backward sweep, as in k_sell3.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBW = 4; // warps (= blocks of rows) per CTA
+
+int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
+
+static size_t bsell_warp_bytes(int bs, int max_int)
+{ // acc[32*bs] doubles | ival[max_int] doubles | ioff[33] ushort (72 B) | icol[max_int] bytes
+  const size_t b = size_t(32) * bs * 8 + size_t(max_int) * 8 + 72 + size_t(max_int);
+  return (b + 15) & ~size_t(15);
+}
+
+template <int BS>
+__device__ __forceinline__ void bsell_gather(const double *yp, int c, double (&x)[BS])
+{
+  if constexpr (BS == 3) ld256(yp + 4 * int64_t(c), x[0], x[1], x[2]);
+  else if constexpr (BS == 2) {
+    double a, b;
+    asm("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(yp + 2 * int64_t(c)));
+    x[0] = a; x[1] = b;
+  } else {
+    double a;
+    asm("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(yp + c));
+    x[0] = a;
+  }
+}
+
+// DIR 0: forward substitution  y = x - L y          (unit diagonal, Ifpack: L scaled by dinv_j)
+// DIR 1: backward substitution y = y * dinv - U y   (Ifpack: U scaled by dinv_i), also stored to io->y
+template <int BS, int DIR>
+__global__ void __launch_bounds__(kBW * 32) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
+                                                    const int *__restrict__ e_ptr, const int *__restrict__ e_col,
+                                                    const unsigned char *__restrict__ e_row,
+                                                    const double *__restrict__ e_val, const int *__restrict__ i_ptr,
+                                                    const unsigned short *__restrict__ i_off,
+                                                    const unsigned char *__restrict__ i_col,
+                                                    const double *__restrict__ i_val, double *yp,
+                                                    const double *__restrict__ dinv, const int *__restrict__ order,
+                                                    const TrsvIo *__restrict__ io, int max_int, int warp_bytes)
+{
+  constexpr int PS = BS == 3 ? 4 : BS;
+  constexpr int U = 4;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char bsell_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = b0 + blockIdx.x * kBW + warp;
+  if (b >= b1) return; // the whole warp leaves; there is no block-wide barrier below
+  unsigned char *base = bsell_smem + size_t(warp) * warp_bytes;
+  double *acc = reinterpret_cast<double *>(base);
+  double *sval = acc + 32 * BS;
+  unsigned short *soff = reinterpret_cast<unsigned short *>(sval + max_int);
+  unsigned char *scol = reinterpret_cast<unsigned char *>(soff) + 72;
+  const int r0 = blk_row[b], nr = blk_row[b + 1] - r0;
+  const int row = r0 + lane;
+  const bool valid = lane < nr;
+  double res[BS];
+#pragma unroll
+  for (int d = 0; d < BS; ++d) res[d] = 0.0;
+  int ro = 0;
+  if (valid) {
+    ro = order[row];
+    if (DIR == 0) {
+      const double *xi = io->x + int64_t(BS) * ro;
+#pragma unroll
+      for (int d = 0; d < BS; ++d) res[d] = xi[d];
+    } else {
+      const double di = dinv[row];
+      const double *yi = yp + int64_t(PS) * row;
+#pragma unroll
+      for (int d = 0; d < BS; ++d) res[d] = yi[d] * di;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < BS; ++d) acc[lane * BS + d] = 0.0;
+  const int ib = i_ptr[b], ni = i_ptr[b + 1] - ib;
+  for (int k = lane; k < ni; k += 32) {
+    sval[k] = __ldcs(i_val + ib + k);
+    scol[k] = i_col[ib + k];
+  }
+  for (int k = lane; k < 33; k += 32) soff[k] = i_off[size_t(b) * 33 + k];
+  // ---- entries coupling with other blocks: software-pipelined stream + segmented scan per row
+  const int eb = e_ptr[b], ng = (e_ptr[b + 1] - eb) >> 5;
+  const int *cp = e_col + eb + lane;
+  const unsigned char *rp = e_row + eb + lane;
+  const double *vp = e_val + eb + lane;
+  int c[U], nc[U], rw[U], nrw[U];
+  double v[U], nv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const bool ok = u < ng;
+    c[u] = ok ? __ldcs(cp + u * 32) : 0;
+    rw[u] = ok ? int(rp[u * 32]) : 0;
+    v[u] = ok ? __ldcs(vp + u * 32) : 0.0;
+  }
+  __syncwarp();
+  for (int g = 0; g < ng; g += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = g + U + u < ng;
+      nc[u] = ok ? __ldcs(cp + (g + U + u) * 32) : 0;
+      nrw[u] = ok ? int(rp[(g + U + u) * 32]) : 0;
+      nv[u] = ok ? __ldcs(vp + (g + U + u) * 32) : 0.0;
+    }
+    double x[U][BS];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (g + u < ng) bsell_gather<BS>(yp, c[u], x[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g + u < ng) { // warp-uniform
+        double p[BS];
+#pragma unroll
+        for (int d = 0; d < BS; ++d) p[d] = v[u] * x[u][d];
+        const int key = rw[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int kk = __shfl_up_sync(FULL, key, o);
+          const bool take = lane >= o && kk == key;
+#pragma unroll
+          for (int d = 0; d < BS; ++d) {
+            const double t = __shfl_up_sync(FULL, p[d], o);
+            if (take) p[d] += t;
+          }
+        }
+        const int kn = __shfl_down_sync(FULL, key, 1);
+        if (lane == 31 || kn != key) {
+#pragma unroll
+          for (int d = 0; d < BS; ++d) acc[key * BS + d] += p[d];
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { c[u] = nc[u]; rw[u] = nrw[u]; v[u] = nv[u]; }
+  }
+#pragma unroll
+  for (int d = 0; d < BS; ++d) res[d] -= acc[lane * BS + d];
+  // ---- entries inside the block: sequential elimination, finished rows broadcast by shuffle
+  if (ni > 0) {
+    int p = valid ? int(soff[lane]) : 0;
+    const int pe = valid ? int(soff[lane + 1]) : 0;
+    int cc = p < pe ? int(scol[p]) : 255;
+    double cv = p < pe ? sval[p] : 0.0;
+#pragma unroll 4
+    for (int step = 0; step < 32; ++step) {
+      const int r = DIR == 0 ? step : 31 - step;
+      if (r >= nr) continue; // warp-uniform
+      double y[BS];
+#pragma unroll
+      for (int d = 0; d < BS; ++d) y[d] = __shfl_sync(FULL, res[d], r);
+      if (cc == r) {
+#pragma unroll
+        for (int d = 0; d < BS; ++d) res[d] -= cv * y[d];
+        ++p;
+        if (p < pe) { cc = int(scol[p]); cv = sval[p]; }
+        else cc = 255;
+      }
+    }
+  }
+  if (valid) {
+    double *o = yp + int64_t(PS) * row;
+#pragma unroll
+    for (int d = 0; d < BS; ++d) o[d] = res[d];
+    if (BS == 3 && DIR == 0) o[3] = 0.0;
+    if (DIR == 1) {
+      double *yo = io->y + int64_t(BS) * ro;
+#pragma unroll
+      for (int d = 0; d < BS; ++d) yo[d] = res[d];
+    }
+  }
+}
+
+static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<int> &colind,
+                            const std::vector<int> &diagpos, const std::vector<int> &blk_ptr, bool lower, DevBsell &out)
+{
+  const int nb = int(blk_ptr.size()) - 1;
+  std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), e_col, e_map, i_map;
+  std::vector<unsigned char> e_row, i_col;
+  std::vector<unsigned short> i_off(size_t(nb) * 33, 0);
+  e_col.reserve(colind.size() / 2);
+  e_map.reserve(colind.size() / 2);
+  e_row.reserve(colind.size() / 2);
+  int max_int = 0;
+  int64_t n_ext = 0;
+  std::vector<std::pair<int, int>> tmp;
+  for (int b = 0; b < nb; ++b) {
+    const int r0 = blk_ptr[b], r1 = blk_ptr[b + 1];
+    if (r1 - r0 > 32) throw StateError("bsell: block with more than 32 rows");
+    const size_t ebase = e_col.size();
+    for (int r = r0; r < r1; ++r) {
+      const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
+      for (int e = a; e < z; ++e) {
+        const int c = colind[e];
+        const bool intra = lower ? (c >= r0) : (c < r1);
+        if (!intra) { e_col.push_back(c); e_row.push_back((unsigned char)(r - r0)); e_map.push_back(e); ++n_ext; }
+      }
+    }
+    if (e_col.size() > ebase) // pad with zero-valued copies of the last entry (a final, valid column)
+      while ((e_col.size() - ebase) % 32) { e_col.push_back(e_col.back()); e_row.push_back(e_row.back()); e_map.push_back(-1); }
+    if (e_col.size() > size_t(0x7fffffff)) throw StateError("bsell: more than 2^31 slots");
+    e_ptr[b + 1] = int(e_col.size());
+    const size_t ibase = i_col.size();
+    for (int lr = 0; lr < 32; ++lr) {
+      i_off[size_t(b) * 33 + lr] = (unsigned short)(i_col.size() - ibase);
+      const int r = r0 + lr;
+      if (r >= r1) continue;
+      const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
+      tmp.clear();
+      for (int e = a; e < z; ++e) {
+        const int c = colind[e];
+        const bool intra = lower ? (c >= r0) : (c < r1);
+        if (intra) tmp.emplace_back(c - r0, e);
+      }
+      if (!lower) std::reverse(tmp.begin(), tmp.end()); // descending columns for the backward sweep
+      for (auto &ce : tmp) { i_col.push_back((unsigned char)ce.first); i_map.push_back(ce.second); }
+    }
+    i_off[size_t(b) * 33 + 32] = (unsigned short)(i_col.size() - ibase);
+    max_int = std::max(max_int, int(i_col.size() - ibase));
+    i_ptr[b + 1] = int(i_col.size());
+  }
+  out.n_blocks = nb;
+  out.max_int = max_int;
+  out.n_ext = int64_t(e_col.size());
+  out.n_int = int64_t(i_col.size());
+  (void)n_ext;
+  out.e_ptr.upload(e_ptr); out.e_col.upload(e_col); out.e_map.upload(e_map); out.e_row.upload(e_row);
+  out.e_val.alloc(e_col.size());
+  out.i_ptr.upload(i_ptr); out.i_map.upload(i_map); out.i_off.upload(i_off); out.i_col.upload(i_col);
+  out.i_val.alloc(i_col.size());
+}
+
+void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
+                 const std::vector<int> &diagpos, const std::vector<int> &blk_ptr, const std::vector<int> &colour_blk)
+{
+  ilu.blk_row.upload(blk_ptr);
+  ilu.colour_blk = colour_blk;
+  bsell_build_one(rowptr, colind, diagpos, blk_ptr, true, ilu.bL);
+  bsell_build_one(rowptr, colind, diagpos, blk_ptr, false, ilu.bU);
+}
+
+void bsell_fill(Handle &H, DevIlu &ilu)
+{
+  auto fill = [&](int64_t n, const int *map, double *val) {
+    if (n == 0) return;
+    k_sell_fill<<<unsigned(std::min<int64_t>((n + 255) / 256, kSM * 16)), 256, 0, H.stream>>>(n, map, ilu.val.p, val);
+    H.launches++;
+  };
+  fill(ilu.bL.n_ext, ilu.bL.e_map.p, ilu.bL.e_val.p);
+  fill(ilu.bL.n_int, ilu.bL.i_map.p, ilu.bL.i_val.p);
+  fill(ilu.bU.n_ext, ilu.bU.e_map.p, ilu.bU.e_val.p);
+  fill(ilu.bU.n_int, ilu.bU.i_map.p, ilu.bU.i_val.p);
+}
+
+template <int BS, int DIR>
+static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, int b0, int b1, double *yp, const TrsvIo *io)
+{
+  const size_t wb = bsell_warp_bytes(BS, B.max_int);
+  const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
+  k_bsell<BS, DIR><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_col.p, B.e_row.p, B.e_val.p,
+                                                     B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, yp, ilu.dinv.p,
+                                                     ilu.order.p, io, B.max_int, int(wb));
+}
+
+template <int BS>
+static void bsell_trsv_t(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
+{
+  const int nc = int(ilu.colour_blk.size()) - 1;
+  const TrsvIo *io = reinterpret_cast<const TrsvIo *>(ilu.io.p);
+  for (int c = 0; c < nc; ++c) {
+    const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
+    if (b <= a) continue;
+    launch_bsell<BS, 0>(s, ilu, ilu.bL, a, b, yp, io);
+    H.launches++;
+  }
+  for (int c = nc - 1; c >= 0; --c) {
+    const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
+    if (b <= a) continue;
+    launch_bsell<BS, 1>(s, ilu, ilu.bU, a, b, yp, io);
+    H.launches++;
+  }
+}
+
+// yp: staging vector in factor order (bsell_stride doubles per row); in / out through ilu.io
+void bsell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
+{
+  if (ilu.bs_rhs == 3) bsell_trsv_t<3>(H, ilu, yp, s);
+  else if (ilu.bs_rhs == 2) bsell_trsv_t<2>(H, ilu, yp, s);
+  else bsell_trsv_t<1>(H, ilu, yp, s);
+  NSB_CUDA(cudaGetLastError());
+}
+
 void sell_set_io(Handle &H, DevIlu &ilu, const double *x, double *y)
 {
   k_set_io<<<1, 1, 0, H.stream>>>(reinterpret_cast<TrsvIo *>(ilu.io.p), x, y);

@@ -802,6 +802,11 @@ extern "C" double nsb_stat(nsb_handle h, const char *name)
   if (n == "nnz_iluF") return double(H.iluF.nnz);
   if (n == "nnz_iluS") return double(H.iluS.nnz);
   if (n == "p2p") return halo_is_p2p(H) ? 1.0 : 0.0;
+  // dependent launches of one triangular solve (forward or backward)
+  if (n == "sweeps_F") return double(H.iluF.colour_ptr.size() > 1 ? H.iluF.colour_ptr.size() - 1 : H.iluF.lvl_ptr_f.size() - 1);
+  if (n == "sweeps_S") return double(H.iluS.colour_ptr.size() > 1 ? H.iluS.colour_ptr.size() - 1 : H.iluS.lvl_ptr_f.size() - 1);
+  if (n == "ilu_blocks_F") return double(H.iluF.bL.n_blocks);
+  if (n == "ilu_blocks_S") return double(H.iluS.bL.n_blocks);
   if (n == "levels_F_fwd") return double(H.iluF.lvl_ptr_f.size()) - 1;
   if (n == "levels_F_bwd") return double(H.iluF.lvl_ptr_b.size()) - 1;
   if (n == "levels_S_fwd") return double(H.iluS.lvl_ptr_f.size()) - 1;

@@ -103,6 +103,23 @@ struct DevSell {
   std::vector<int> range_slice; // first slice of each row range (colour)
 };
 
+// Block-sequential storage of one triangular factor in the block multicolour ordering (kernels_sell.cu,
+// "bsell"): a block is <= 32 consecutive factor rows solved by one warp.  Entries that couple with other
+// blocks ("ext", all of them final when the block's colour is swept) are packed block by block, sorted
+// by row, padded to a multiple of 32 per block, and reduced per row by a segmented warp scan; entries
+// inside the block ("int") are packed row by row and resolved sequentially by shuffle broadcast.
+struct DevBsell {
+  int n_blocks = 0, max_int = 0;    // max_int: most intra-block entries of any block
+  int64_t n_ext = 0, n_int = 0;
+  DevBuf<int> e_ptr, e_col, e_map;  // e_ptr[b]: first ext slot of block b (multiple of 32)
+  DevBuf<unsigned char> e_row;      // local row (0..31) of each ext slot
+  DevBuf<double> e_val;
+  DevBuf<int> i_ptr, i_map;         // i_ptr[b]: first intra entry of block b
+  DevBuf<unsigned short> i_off;     // [n_blocks][33] offsets of each local row inside the block's entries
+  DevBuf<unsigned char> i_col;      // local column (0..31); ascending per row (L), descending (U)
+  DevBuf<double> i_val;
+};
+
 // ILU(0) factors in Ifpack's storage convention (strict lower part = a_ij * dinv_j, strict upper
 // part scaled by dinv_i, inverse diagonal separate), on the owned-columns pattern, plus the
 // level schedules of the two triangular solves.
@@ -115,8 +132,11 @@ struct DevIlu {
   std::vector<int> h_order;
   DevBuf<double> val, dinv;
   // multicolour mode: split L / U factors and per-colour row blocks for the CSR-stream solves
-  bool stream = false, sell = false;
+  bool stream = false, sell = false, bsell = false;
   DevSell sellL, sellU;
+  DevBsell bL, bU;                // block multicolour mode (ilu_ordering = 2)
+  DevBuf<int> blk_row;            // first factor row of each block, [n_blocks + 1]
+  std::vector<int> colour_blk;    // first block of each block colour
   DevBuf<double> io;              // TrsvIo slot: caller's in / out pointers of the captured solve
   DevBuf<int> Lp, Lc, Up, Uc, mapL, mapU, blkL, blkU;
   DevBuf<double> Lv, Uv;
@@ -352,6 +372,12 @@ void sell_fill(Handle &H, DevSell &S, const double *src);
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
 void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
 void sell_set_io(Handle &H, DevIlu &ilu, const double *x, double *y);
+// block multicolour ILU(0) solves
+void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
+                 const std::vector<int> &diagpos, const std::vector<int> &blk_ptr, const std::vector<int> &colour_blk);
+void bsell_fill(Handle &H, DevIlu &ilu);
+int bsell_stride(int bs_rhs); // doubles per row of the staging vector
+void bsell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
 
 // ---------------------------------------------------------------- solver.cu
 void solver_alloc(Handle &H);

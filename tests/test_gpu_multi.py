@@ -18,6 +18,18 @@ def _free_port():
     return p
 
 
+def _solver_overrides(case_name):
+    """The 1 093-DoF Ethier-Steinman cube split into subdomains is a STAGNATING solve at the reference's
+    inner tolerance 1e-2 (110-300 outer iterations of GMRES(28) for a system of 1 093 unknowns): its
+    iteration count is round-off noise -- the oracle alone gives 26 or 24 iterations for step 3 depending
+    on its OpenMP thread count, and 248 or 305 for step 1 between two runs on the GPU box
+    (profiles/r02_multi_gpu.md) -- which is what made the round-1 `cube-1-p2p` case fail, not the
+    transport.  With the inner solves tightened to 1e-6 the preconditioner is (nearly) a fixed operator,
+    the solve takes 13 / 13 / 4 iterations on any summation order, and the case tests what it is meant to:
+    the CONV variant (Neumann rhs, exact-solution Dirichlet rows, non-zero initial state) across ranks."""
+    return {"inner_rtol": 1e-6} if case_name == "cube" else {}
+
+
 def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
     import sys
 
@@ -42,7 +54,7 @@ def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
         case = T.Case(case_name)
         prob = DistributedNavierStokes(case.mesh, case.variant, T=1.0, deltat=case.dt, test_case=2 if case.dim == 3 else 3,
                                        device=rank, nranks=world, rank=rank, unique_id=uid[0], ilu_ordering=ordering,
-                                       orthogonalisation=orth)
+                                       orthogonalisation=orth, **_solver_overrides(case_name))
         prob.setup()
         e = prob.engine
         assert prob.transport == transport and e.stat("p2p") == (1.0 if transport == "p2p" else 0.0), prob.transport
@@ -116,6 +128,8 @@ def test_ranks_match_block_jacobi_oracle(case_name, ordering, orth, transport, w
     o = case.oracle()
     o.set_partition(part)
     o.set_orthogonalisation(orth)
+    if _solver_overrides(case_name):
+        o.set_options(**_solver_overrides(case_name))
     if ordering >= 1:
         # global ILU ordering = each rank's multicolour order of its owned block, rank after rank
         ou, op = [], []

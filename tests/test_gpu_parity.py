@@ -231,13 +231,15 @@ def _oracle_order(case, e):
     return ou, e.ilu_order(1)
 
 
+@pytest.mark.parametrize("ordering", [1, 2])
 @pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cube", "yosida"),
                                              ("cyl3d", "yosida"), ("box2d", "simple"), ("box3d", "ayosida")])
-def test_multicolour_ilu_mode(case_name, ptype):
-    """Throughput mode (ilu_ordering = 1): ILU(0) of the multicolour-permuted matrices.  Same
-    checks as the replay mode, against the oracle factorising in the same ordering."""
+def test_multicolour_ilu_mode(case_name, ptype, ordering):
+    """Throughput modes (ilu_ordering = 1: point multicolour, 2: block multicolour with sequential
+    elimination inside 32-row blocks): ILU(0) of the permuted matrices.  Same checks as the replay
+    mode, against the oracle factorising in the same ordering."""
     case = T.Case(case_name)
-    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1)
+    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=ordering)
     ou, op = _oracle_order(case, e)
     assert sorted(ou.tolist()) == list(range(case.n_u)) and sorted(op.tolist()) == list(range(case.n_p))
     assert not np.array_equal(op, np.arange(case.n_p))
@@ -273,19 +275,20 @@ def test_multicolour_ilu_mode(case_name, ptype):
         assert rc == 0 and its_e == its_o, (step, its_e, its_o)
         xo, xe = o.array("sol_owned", case.N), e.get_solution()
         assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < FIELD_TOL, step
-    # far fewer dependency levels than the natural ordering
-    assert e.stat("levels_F_fwd") <= 40 and e.stat("levels_S_fwd") <= 80
+    # far fewer dependent launches per triangular solve than the natural ordering has levels
+    assert e.stat("sweeps_F") <= 40 and e.stat("sweeps_S") <= 80
 
 
+@pytest.mark.parametrize("ordering", [1, 2])
 @pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cyl3d", "yosida"),
                                              ("cube", "yosida")])
-def test_batched_gram_schmidt_mode(case_name, ptype):
+def test_batched_gram_schmidt_mode(case_name, ptype, ordering):
     """Throughput mode of the Krylov solvers (orthogonalisation = 1): classical Gram-Schmidt with all
     coefficients of an Arnoldi step from one fused multi-dot (inner solves: deal.II's loss test on
     every vector; outer solve: two passes), on top of the multicolour ILU(0).  Checked against the
     oracle running the same variant: same iteration counts, fields within 1e-8."""
     case = T.Case(case_name)
-    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=1, orthogonalisation=1)
+    o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=ordering, orthogonalisation=1)
     o.set_ilu_order(*_oracle_order(case, e))
     o.set_orthogonalisation(1)
     rows, vals = case.bc(0.0)
