@@ -49,6 +49,16 @@ static int guarded(nsb_handle h, Fn &&fn)
 }
 
 static void sync(Handle &H) { NSB_CUDA(cudaStreamSynchronize(H.stream)); }
+// Host -> device copy ordered on the engine's stream.  H.stream is a non-blocking stream, so a plain
+// cudaMemcpy (legacy default stream) is NOT ordered against it, and for pageable memory cudaMemcpy may
+// return while the DMA of its last staging chunk is still in flight: kernels launched on H.stream right
+// afterwards could read the tail of the previous content.
+static void h2d(Handle &H, void *dst, const void *src, size_t bytes)
+{
+  if (!bytes) return;
+  NSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, H.stream));
+  sync(H);
+}
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int nsb_default_params(nsb_params *p, int variant)
@@ -456,6 +466,7 @@ extern "C" int nsb_set_dirichlet(nsb_handle h, int32_t n_rows, const int32_t *ro
     H.d_dir_vals.alloc(std::max<size_t>(1, H.h_dir_nodes.size() * dim));
     H.d_dir_vals.zero();
     H.h_dir_vals.assign(H.h_dir_nodes.size() * dim, 0.0);
+    NSB_CUDA(cudaDeviceSynchronize()); // uploads / memsets above ran on the default stream, kernels use H.stream
   });
 }
 
@@ -475,7 +486,7 @@ extern "C" int nsb_set_neumann_rhs(nsb_handle h, const double *rhs_u)
   return guarded(h, [&](Handle &H) {
     if (!H.finalized) throw StateError("setup not finalized");
     if (!rhs_u) { H.have_neumann = false; return; }
-    NSB_CUDA(cudaMemcpy(H.d_neumann.p, rhs_u, sizeof(double) * H.nu_owned(), cudaMemcpyHostToDevice));
+    h2d(H, H.d_neumann.p, rhs_u, sizeof(double) * H.nu_owned());
     H.have_neumann = true;
   });
 }
@@ -507,7 +518,7 @@ static void upload_vec(Handle &H, const double *x, double *dev)
   }
   std::vector<double> t;
   to_device_layout(H, x, t);
-  NSB_CUDA(cudaMemcpy(dev, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
+  h2d(H, dev, t.data(), sizeof(double) * t.size());
 }
 static void download_vec(Handle &H, const double *dev, double *x)
 {
@@ -720,7 +731,7 @@ extern "C" int nsb_op_block_vmult(nsb_handle h, int blk, const double *x, double
     double *in = H.ws->prec_in.p, *out = H.ws->prec_out.p;
     const int nin = (blk == NSB_BLK_F || blk == NSB_BLK_B) ? nu : np;
     const int nout = (blk == NSB_BLK_F || blk == NSB_BLK_BT) ? nu : np;
-    NSB_CUDA(cudaMemcpy(in, x, sizeof(double) * nin, cudaMemcpyHostToDevice));
+    h2d(H, in, x, sizeof(double) * nin);
     if (blk == NSB_BLK_F) spmv_F(H, in, 0, nullptr, 0, out);
     else if (blk == NSB_BLK_BT) spmv_Bt(H, in, 0, out);
     else if (blk == NSB_BLK_B) spmv_B(H, in, 0, out);
@@ -747,7 +758,7 @@ extern "C" int nsb_op_ilu_apply(nsb_handle h, int which, const double *x, double
     DevIlu &ilu = which == 0 ? H.iluF : H.iluS;
     const int n = ilu.n * ilu.bs_rhs;
     double *in = H.ws->prec_in.p, *out = H.ws->prec_out.p;
-    NSB_CUDA(cudaMemcpy(in, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    h2d(H, in, x, sizeof(double) * n);
     ilu_solve(H, ilu, in, out);
     sync(H);
     NSB_CUDA(cudaMemcpy(y, out, sizeof(double) * n, cudaMemcpyDeviceToHost));
