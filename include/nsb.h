@@ -154,6 +154,20 @@ int nsb_set_dirichlet_values(nsb_handle h, const double *values);
  * system_rhs.block(0) (length n_u, owned part used); NULL clears it. */
 int nsb_set_neumann_rhs(nsb_handle h, const double *rhs_u);
 
+/* ---- drag / lift ---------------------------------------------------------------------- */
+/* replaces: the face loop + MPI sum of NavierStokes::compute_forces (src/NavierStokes2D.cpp:752-859:
+ * QGauss<1>(3), forces = (nu grad u - p I)(-n) JxW; src/NavierStokes3D.cpp:744-840: QGaussSimplex<2>(3),
+ * tangential formula with t = (n_y, -n_x, 0)) on the device, so that solve() no longer copies the whole
+ * solution to the host every step.  nsb_set_force_faces (once, after nsb_set_mesh): the obstacle faces
+ * (boundary id 3) of LOCALLY OWNED cells -- face k lies in local cell face_cell[k] opposite to its local
+ * vertex face_local[k] (the pairs nsh_dofs_boundary_faces returns) -- and the face rule on the unit face
+ * (xi[n_q][dim-1], weights summing to 1 in 2D, 1/2 in 3D).  nsb_compute_forces: out[0] = drag,
+ * out[1] = lift of the current solution, the raw integrals summed over all ranks (collective: every rank
+ * calls it; the c_d / c_l scaling by the mean velocity stays with the caller). */
+int nsb_set_force_faces(nsb_handle h, int32_t n_faces, const int32_t *face_cell, const int32_t *face_local,
+                        int32_t n_q, const double *xi, const double *w);
+int nsb_compute_forces(nsb_handle h, double rho, double *out);
+
 /* ---- state ---------------------------------------------------------------------------- */
 /* replaces: VectorTools::interpolate(u_0) -> solution_owned; solution = solution_owned
  * (src/NavierStokes2D.cpp:708-709).  x has n_u + n_p entries [u block | p block] (local). */

@@ -47,6 +47,8 @@ SIGNATURES = {
     "nsb_set_dirichlet": (C.c_int, [_H, C.c_int32, c_int_p]),
     "nsb_set_dirichlet_values": (C.c_int, [_H, c_double_p]),
     "nsb_set_neumann_rhs": (C.c_int, [_H, c_double_p]),
+    "nsb_set_force_faces": (C.c_int, [_H, C.c_int32, c_int_p, c_int_p, C.c_int32, c_double_p, c_double_p]),
+    "nsb_compute_forces": (C.c_int, [_H, C.c_double, c_double_p]),
     "nsb_set_solution": (C.c_int, [_H, c_double_p]),
     "nsb_get_solution": (C.c_int, [_H, c_double_p]),
     "nsb_assemble_first": (C.c_int, [_H, C.c_double]),

@@ -167,6 +167,11 @@ void NavierStokes::setup()
   check(nsb_set_quadrature(engine, q.size(), q.xi.data(), q.w.data()), "nsb_set_quadrature");
   check(nsb_finalize_setup(engine), "nsb_finalize_setup");
   check(nsb_set_dirichlet(engine, int32_t(dir_rows.size()), dir_rows.data()), "nsb_set_dirichlet");
+  if (variant != Variant::Convergence3D) { // compute_forces runs on the device: obstacle faces + face rule
+    const Rule qf = gauss_simplex(dim - 1); // QGauss<1>(3) (NavierStokes2D.cpp:758) / QGaussSimplex<2>(3)
+    check(nsb_set_force_faces(engine, nf, obstacle_cells.data(), obstacle_faces.data(), qf.size(), qf.xi.data(), qf.w.data()),
+          "nsb_set_force_faces");
+  }
   solution.assign(size_t(N), 0.0);
 }
 
@@ -283,15 +288,22 @@ void NavierStokes::solve_time_step(double)
     std::ofstream gm("gmres.csv", std::ios::app);
     if (gm.is_open()) gm << time_now << ',' << Re << ',' << its << "\n";
   }
-  check(nsb_get_solution(engine, solution.data()), "nsb_get_solution"); // solution = solution_owned (:637)
+  solution_stale = true; // solution = solution_owned (:637) stays on the device until a host consumer asks
+}
+
+void NavierStokes::sync_solution() const
+{
+  if (!solution_stale) return;
+  check(nsb_get_solution(engine, solution.data()), "nsb_get_solution");
+  solution_stale = false;
 }
 
 // NavierStokes2D.cpp:752-859 (QGauss<1>(3) on the cylinder edges, force = (nu grad u - p I) n) and
 // NavierStokes3D.cpp:744-840 (QGaussSimplex<2>(3), tangential formula).
 std::vector<double> NavierStokes::compute_forces()
 {
-  double fl[2];
-  check(nsh_boundary_forces(mesh, dofs, solution.data(), 3, nu, rho, fl), "nsh_boundary_forces");
+  double fl[2]; // face integrals + sum over ranks on the device: no solution download
+  check(nsb_compute_forces(engine, rho, fl), "nsb_compute_forces");
   const double drag = fl[0], lift = fl[1];
   const double mean_v = inlet_mean_velocity(dim, test_case, time_now), D = 0.1, H = 0.41;
   const double den = dim == 2 ? mean_v * mean_v * D : rho * mean_v * mean_v * D * H;
@@ -312,6 +324,7 @@ void NavierStokes::output(unsigned time_step, const std::vector<double> &coeff) 
   char num[16];
   std::snprintf(num, sizeof(num), "%03u", time_step);
   const std::string path = dir + name + "_" + num + ".vtu";
+  sync_solution();
   if (nsh_write_vtu(mesh, dofs, solution.data(), path.c_str()) != 0) throw std::runtime_error("cannot write " + path);
   if (verbose) std::cout << "Output written to " << name << std::endl;
   if (variant == Variant::Cylinder2D && coeff.size() >= 2) {
@@ -326,6 +339,7 @@ void NavierStokes::compute_pressure_difference()
 {
   const double pa[3] = {0.45, 0.2, 0.205}, pe[3] = {0.55, 0.2, 0.205};
   double va[4], ve[4];
+  sync_solution();
   const double p1 = nsh_dofs_point_value(dofs, solution.data(), pa, va) == 0 ? va[dim] : 0.0;
   const double p2 = nsh_dofs_point_value(dofs, solution.data(), pe, ve) == 0 ? ve[dim] : 0.0;
   pressure_difference = p1 - p2;
@@ -377,6 +391,7 @@ void NavierStokes::solve()
 // 14-point degree-5 rule is used here (the integrand error is far below the discretisation error).
 double NavierStokes::compute_error(const VectorTools::NormType &norm_type)
 {
+  sync_solution();
   const Rule q = gauss_simplex(3);
   const int32_t *cd = nsh_dofs_cell_dofs(dofs);
   const double *cc = nsh_dofs_cell_coords(dofs);

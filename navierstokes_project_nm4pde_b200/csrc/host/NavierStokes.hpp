@@ -49,7 +49,7 @@ public:
   bool write_output = false; // VTU per step (2D) / every 20 steps (3D), gmres.csv, coeff_2.csv as the reference
   bool verbose = true;
 
-  const std::vector<double> &get_solution() const { return solution; }
+  const std::vector<double> &get_solution() { sync_solution(); return solution; }
   int n_dofs() const { return N; }
 
 protected:
@@ -63,6 +63,7 @@ protected:
   void neumann_rhs(double time, std::vector<double> &rhs) const; // Convergence3D.cpp:309-330
   void initial_condition(std::vector<double> &x) const;          // NavierStokes2D.cpp:708
   void check(int rc, const char *what) const;
+  void sync_solution() const; // device -> host copy of the solution, only when a host consumer needs it
 
   Variant variant;
   int dim;
@@ -79,7 +80,8 @@ protected:
   std::vector<int32_t> dir_nodes, dir_rows;
   std::vector<char> dir_is_inlet;
   std::vector<int32_t> obstacle_cells, obstacle_faces; // boundary id 3: owning cell, local face
-  std::vector<double> solution;
+  mutable std::vector<double> solution; // host mirror of the device solution (see sync_solution)
+  mutable bool solution_stale = false;
   double time_now = 0.0;
 };
 

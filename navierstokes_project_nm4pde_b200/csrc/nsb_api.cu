@@ -491,6 +491,26 @@ extern "C" int nsb_set_neumann_rhs(nsb_handle h, const double *rhs_u)
   });
 }
 
+// ---- drag / lift on the device (kernels_post.cu) ---------------------------------------------
+extern "C" int nsb_set_force_faces(nsb_handle h, int32_t n_faces, const int32_t *face_cell, const int32_t *face_local,
+                                   int32_t n_q, const double *xi, const double *w)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!H.have_mesh) throw StateError("nsb_set_force_faces before nsb_set_mesh");
+    if (n_faces > 0 && (!face_cell || !face_local)) throw ArgError("nsb_set_force_faces: null face arrays");
+    if (!xi || !w) throw ArgError("nsb_set_force_faces: null quadrature");
+    force_faces_set(H, n_faces, face_cell, face_local, n_q, xi, w);
+  });
+}
+extern "C" int nsb_compute_forces(nsb_handle h, double rho, double *out)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!H.finalized) throw StateError("setup not finalized");
+    if (!out) throw ArgError("nsb_compute_forces: null output");
+    force_faces_compute(H, rho, out);
+  });
+}
+
 // ---- vectors: caller layout [u (owned, ghost) | p (owned, ghost)] <-> device layout -----------
 static void to_device_layout(Handle &H, const double *x, std::vector<double> &out)
 {

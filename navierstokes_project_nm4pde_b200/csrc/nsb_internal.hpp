@@ -283,6 +283,14 @@ struct Handle {
   DevBuf<double> d_neumann;
   bool have_neumann = false;
 
+  // ---- device: obstacle faces of compute_forces (kernels_post.cu), face-minor arrays
+  int n_force_faces = 0, force_nq = 0;
+  DevBuf<double> d_ff_x;          // [(dim+1)*dim][n_faces] vertex coordinates of the face's cell
+  DevBuf<int> d_ff_nodes, d_ff_p; // [n2][n_faces], [nv1][n_faces]
+  DevBuf<int> d_ff_opp;           // [n_faces] local vertex opposite to the face
+  DevBuf<double> d_ff_q;          // xi[nq][dim-1], w[nq]
+  DevBuf<double> d_ff_part;       // [2][n_faces] per-face drag / lift, then the two sums
+
   // ---- device: vectors (local layout)
   DevBuf<double> d_sol, d_rhs;
   DevBuf<double> d_scratch;       // reductions etc.
@@ -378,6 +386,10 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
 void bsell_fill(Handle &H, DevIlu &ilu);
 int bsell_stride(int bs_rhs); // doubles per row of the staging vector
 void bsell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
+
+// ---------------------------------------------------------------- kernels_post.cu
+void force_faces_set(Handle &H, int nf, const int *face_cell, const int *face_opp, int nq, const double *xi, const double *w);
+void force_faces_compute(Handle &H, double rho, double *out);
 
 // ---------------------------------------------------------------- solver.cu
 void solver_alloc(Handle &H);

@@ -164,6 +164,12 @@ class DistributedNavierStokes(NavierStokes):
             self._inlet_mask = self._inlet_mask[keep]
         self._dir_rows = (dim * self._dir_nodes[:, None] + np.arange(dim)[None, :]).ravel().astype(np.int32)
         e.set_dirichlet(self._dir_rows)
+        if self.variant != "conv":  # compute_forces: obstacle faces of the cells this rank owns (is_locally_owned)
+            fc, fl = d.boundary_faces(3)
+            mine = cell_part[fc] == self.rank
+            g2l_cell = np.full(d.n_cells, -1, np.int64)
+            g2l_cell[loc["cells"]] = np.arange(loc["cells"].size)
+            e.set_force_faces(g2l_cell[fc[mine]], fl[mine], *gauss_simplex(dim - 1, self.rule))
         # local sizes in the caller layout [u (owned, ghost) | p (owned, ghost)]
         self.n_u, self.n_p, self.N = dim * nn, npl, dim * nn + npl
         return self

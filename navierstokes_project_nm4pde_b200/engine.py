@@ -320,6 +320,22 @@ class Engine:
             r = np.ascontiguousarray(rhs_u, dtype=np.float64)
             self._ck(self.L.nsb_set_neumann_rhs(self.h, dptr(r)))
 
+    def set_force_faces(self, face_cell, face_local, xi, w):
+        """Obstacle faces of locally owned cells + the face rule for compute_forces (once, after set_mesh)."""
+        fc = np.ascontiguousarray(face_cell, dtype=np.int32)
+        fl = np.ascontiguousarray(face_local, dtype=np.int32)
+        xi = np.ascontiguousarray(xi, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        z = np.zeros(1, np.int32)
+        self._ck(self.L.nsb_set_force_faces(self.h, len(fc), iptr(fc if fc.size else z), iptr(fl if fl.size else z),
+                                            len(w), dptr(xi), dptr(w)))
+
+    def compute_forces(self, rho=1.0):
+        """(drag, lift) integrals of NavierStokes::compute_forces of the current solution, summed over ranks."""
+        out = np.zeros(2)
+        self._ck(self.L.nsb_compute_forces(self.h, float(rho), dptr(out)))
+        return out
+
     def set_solution(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.size == self.N

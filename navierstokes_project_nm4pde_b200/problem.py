@@ -120,6 +120,7 @@ class NavierStokes:
         self.vec_drag, self.vec_lift, self.vec_drag_coeff, self.vec_lift_coeff = [], [], [], []
         self.time_prec, self.time_solve, self.gmres_iterations = [], [], []
         self.engine = None
+        self.forces_after, self.c_D_max, self.c_L_min, self.time = 0.1, -999.0, 999.0, 0.0
 
     # ------------------------------------------------------------------ setup()
     def setup_host(self):
@@ -157,6 +158,8 @@ class NavierStokes:
         e.finalize()
         self.nu = e.params.nu
         e.set_dirichlet(self._dir_rows)
+        if self.variant != "conv":  # obstacle faces of compute_forces (boundary id 3)
+            e.set_force_faces(*d.boundary_faces(3), *gauss_simplex(self.dim - 1, self.rule))
         return self
 
     def dirichlet_values(self, time):
@@ -224,6 +227,19 @@ class NavierStokes:
             print(f"Result:  {its} GMRES iterations")
         return its
 
+    def compute_forces(self, time=None, rho=1.0):
+        """NavierStokes::compute_forces (NavierStokes2D.cpp:752-859, NavierStokes3D.cpp:744-840): the face
+        integrals run on the device (nsb_compute_forces, summed over ranks); returns [c_d, c_l] with
+        c = 2 F / (mean_v^2 D) in 2D and 2 F / (rho mean_v^2 D H) in 3D."""
+        drag, lift = self.engine.compute_forces(rho)
+        mean_v = mean_velocity(self.dim, self.time if time is None else time, self.test_case)
+        D, H = 0.1, 0.41
+        den = mean_v * mean_v * D if self.dim == 2 else rho * mean_v * mean_v * D * H
+        c_d, c_l = 2.0 * drag / den, 2.0 * lift / den
+        self.vec_drag.append(drag); self.vec_lift.append(lift)
+        self.vec_drag_coeff.append(c_d); self.vec_lift_coeff.append(c_l)
+        return [c_d, c_l]
+
     def initial_condition(self):
         """VectorTools::interpolate(dof_handler, u_0, solution_owned) (NavierStokes2D.cpp:708)."""
         x = np.zeros(self.N)
@@ -250,6 +266,11 @@ class NavierStokes:
             else:
                 self.assemble_time_step(time)
             self.solve_time_step(time)
+            self.time = time
+            # NavierStokes2D.cpp:736-740 (every step), NavierStokes3D.cpp:728-733 (only once time > 0.1)
+            if self.variant == "2d" or (self.variant == "3d" and time > self.forces_after):
+                c = self.compute_forces(time)
+                self.c_D_max, self.c_L_min = max(self.c_D_max, c[0]), min(self.c_L_min, c[1])
             if max_steps is not None and step >= max_steps:
                 break
         self.time, self.n_steps = time, step

@@ -1284,6 +1284,106 @@ NSO_API int nso_solve_step(nso_ctx *c, int ptype, int *outer_its, double *last_r
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* NavierStokes::compute_forces -- the face loop over the obstacle boundary (id 3)             */
+/*   2D  src/NavierStokes2D.cpp:752-859   QGauss<1>(3) (the caller passes the rule);           */
+/*        forces = (nu grad u - p I) * (-n) * JxW, drag += forces[0], lift += forces[1]        */
+/*   3D  src/NavierStokes3D.cpp:744-840   QGaussSimplex<2>(3); n = -normal, t = (n_y,-n_x,0)   */
+/*        drag += (rho nu (n . grad u . t/|t|^2) n_y - p n_x) JxW                              */
+/*        lift -= (rho nu (n . grad u . t/|t|^2) n_x + p n_y) JxW                              */
+/* FEFaceValues [deal.II, restated] on an affine simplex: the face quadrature points are       */
+/* embedded into the reference cell, shape gradients are J^{-T} grad_ref, the outward normal   */
+/* is J^{-T} n_ref normalised and the surface element is |det J| |J^{-T} n_ref| dS_ref.  The   */
+/* face is named by the local vertex OPPOSITE to it (the convention of nsh_dofs_boundary_faces */
+/* in include/nsb.h); the rules are symmetric, so the vertex order inside the face is moot.    */
+/* xi_f: nqf points of the unit face ([0,1] or the unit triangle), w_f sums to its measure.    */
+/* out[0] = drag, out[1] = lift (raw integrals; the c_d / c_l scaling stays with the caller).  */
+/* ------------------------------------------------------------------------------------------ */
+NSO_API void nso_compute_forces(const nso_ctx *c, const double *solution, int nf, const int *face_cell,
+                                const int *face_opp, int nqf, const double *xi_f, const double *w_f, double rho,
+                                double *out)
+{
+  const int dim = c->dim, nv = dim + 1, n2 = c->n2, dpc = c->dpc;
+  double local_drag = 0.0, local_lift = 0.0;
+  ldof_t ld;
+  fill_ldof(dim, dpc, &ld);
+  for (int f = 0; f < nf; ++f) {
+    const int cell = face_cell[f], opp = face_opp[f];
+    const double *vc = c->vcoords + (size_t)cell * nv * dim;
+    const int *dofs = c->cell_dofs + (size_t)cell * dpc;
+    double Jinv[3][3];
+    const double det = affine_map(dim, vc, Jinv);
+    /* reference vertices: v0 = 0, vk = e_{k-1}; outward reference normal and dS_ref scale of the face */
+    int fv[3], nfv = 0;
+    for (int v = 0; v < nv; ++v)
+      if (v != opp) fv[nfv++] = v;
+    double nref[3] = {0, 0, 0}, sref = 1.0;
+    if (opp == 0) {
+      for (int d = 0; d < dim; ++d) nref[d] = 1.0 / sqrt((double)dim);
+      sref = sqrt((double)dim); /* |face| / |unit face|: sqrt(2) (edge), sqrt(3) (triangle) */
+    } else
+      nref[opp - 1] = -1.0;
+    double nphys[3] = {0, 0, 0}, nn = 0.0; /* J^{-T} n_ref */
+    for (int d = 0; d < dim; ++d) {
+      for (int k = 0; k < dim; ++k) nphys[d] += Jinv[k][d] * nref[k];
+      nn += nphys[d] * nphys[d];
+    }
+    nn = sqrt(nn);
+    for (int d = 0; d < dim; ++d) nphys[d] /= nn;
+    const double dS = fabs(det) * nn * sref;
+    for (int q = 0; q < nqf; ++q) {
+      /* embed the face point: barycentrics over the face vertices */
+      double lf[3], xr[3] = {0, 0, 0};
+      if (dim == 2) { lf[0] = 1.0 - xi_f[q]; lf[1] = xi_f[q]; }
+      else { lf[0] = 1.0 - xi_f[2 * q] - xi_f[2 * q + 1]; lf[1] = xi_f[2 * q]; lf[2] = xi_f[2 * q + 1]; }
+      for (int i = 0; i < nfv; ++i)
+        if (fv[i] > 0) xr[fv[i] - 1] += lf[i];
+      double phi2[10], dphi2[30], psi[4];
+      nso_tabulate(dim, 1, xr, phi2, dphi2, psi, NULL);
+      /* get_function_gradients / get_function_values of `solution` */
+      double G[3][3] = {{0}}, p = 0.0;
+      for (int i = 0; i < dpc; ++i) {
+        const double u = solution[dofs[i]];
+        const int comp = ld.comp[i], b = ld.base[i];
+        if (comp == dim) { p += u * psi[b]; continue; }
+        for (int d = 0; d < dim; ++d) {
+          double g = 0.0;
+          for (int k = 0; k < dim; ++k) g += dphi2[b * dim + k] * Jinv[k][d];
+          G[comp][d] += u * g;
+        }
+      }
+      (void)n2;
+      const double JxW = w_f[q] * dS;
+      double n[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) n[d] = -nphys[d]; /* normal_vector = -fe_face_values.normal_vector(q) */
+      if (dim == 2) {
+        double forces[2];
+        for (int i = 0; i < 2; ++i) {
+          double s = 0.0;
+          for (int j = 0; j < 2; ++j) s += (c->visc * G[i][j] - (i == j ? p : 0.0)) * n[j];
+          forces[i] = s * JxW;
+        }
+        local_drag += forces[0];
+        local_lift += forces[1];
+      } else {
+        const double nx = n[0], ny = n[1];
+        const double t[3] = {ny, -nx, 0.0};
+        const double t2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        double ngt = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          double ng = 0.0;
+          for (int i = 0; i < 3; ++i) ng += n[i] * G[i][j];
+          ngt += ng * (t[j] / t2);
+        }
+        local_drag += (rho * c->visc * ngt * ny - p * nx) * JxW;
+        local_lift -= (rho * c->visc * ngt * nx + p * ny) * JxW;
+      }
+    }
+  }
+  out[0] = local_drag;
+  out[1] = local_lift;
+}
+
 NSO_API int nso_num_threads(void)
 {
 #ifdef _OPENMP

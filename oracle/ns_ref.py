@@ -508,6 +508,18 @@ class Oracle:
         v = self.array("S_val", nnz)
         return sp.csr_matrix((v, ci, rp), shape=(self.n_p, self.n_p))
 
+    def compute_forces(self, solution, face_cell, face_opp, xi_f, w_f, rho=1.0):
+        """(drag, lift) face integrals of NavierStokes::compute_forces (NavierStokes2D.cpp:752-859,
+        NavierStokes3D.cpp:744-840) of `solution` over the given faces (cell, opposite local vertex)."""
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        fc = np.ascontiguousarray(face_cell, dtype=np.int32)
+        fo = np.ascontiguousarray(face_opp, dtype=np.int32)
+        xi = np.ascontiguousarray(xi_f, dtype=np.float64)
+        w = np.ascontiguousarray(w_f, dtype=np.float64)
+        out = np.zeros(2)
+        self.L.nso_compute_forces(self.h, _dp(sol), len(fc), _ip(fc), _ip(fo), len(w), _dp(xi), _dp(w), C.c_double(rho), _dp(out))
+        return out
+
     def solve_step(self, ptype):
         its, res = C.c_int(0), C.c_double(0.0)
         rc = self.L.nso_solve_step(self.h, PRECOND[ptype], C.byref(its), C.byref(res))

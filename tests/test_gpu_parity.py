@@ -202,6 +202,50 @@ def test_time_steps_fields(case_name, ptype):
         assert np.linalg.norm(xe[nu:] - xo[nu:]) < FIELD_TOL * max(np.linalg.norm(xo[nu:]), np.linalg.norm(xo[:nu])), (step, "pressure")
 
 
+@pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("cyl3d", "yosida")])
+def test_drag_lift_coefficients(case_name, ptype):
+    """f1 / config 3: drag and lift of NavierStokes::compute_forces (NavierStokes2D.cpp:752-859,
+    NavierStokes3D.cpp:744-840) computed ON THE DEVICE (nsb_compute_forces) after each of three time
+    steps against the oracle's restatement evaluated on the oracle's own solution: within 1e-6
+    relative (north_star tolerance); and against the oracle evaluated on the engine's solution
+    (isolates the face kernel from the solver tolerance): 1e-12."""
+    DRAG_LIFT_TOL = 1e-6
+    case = T.Case(case_name)
+    o, e = case.oracle(), case.engine(precond_type=ptype)
+    rows, vals = case.bc(0.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    fc, fl = case.dofs.boundary_faces(3)
+    xi, w = T.gauss_simplex(case.dim - 1)
+    assert len(fc) > 0
+    e.set_force_faces(fc, fl, xi, w)
+    x0 = case.initial()
+    o.set_solution(x0); e.set_solution(x0)
+    t = 0.0
+    for step in range(3):
+        t += case.dt
+        rows, vals = case.bc(2.0 + t)
+        o.set_dirichlet_values(vals); e.set_dirichlet_values(vals)
+        if step == 0:
+            o.assemble_first(); e.assemble_first()
+        else:
+            o.assemble_step(); e.assemble_step()
+        rc, its_o, _ = o.solve_step(ptype)
+        its_e, _, _ = e.solve_step()
+        assert rc == 0 and its_e == its_o
+        f_dev = e.compute_forces(rho=1.0)
+        f_ref = o.compute_forces(o.array("sol_owned", case.N), fc, fl, xi, w, rho=1.0)
+        f_same = o.compute_forces(e.get_solution(), fc, fl, xi, w, rho=1.0)
+        scale = np.abs(f_ref).max()
+        assert np.all(np.abs(f_dev - f_same) <= 1e-12 * scale), (step, f_dev, f_same)
+        assert np.all(np.abs(f_dev - f_ref) <= DRAG_LIFT_TOL * np.abs(f_ref) + 1e-9 * scale), (step, f_dev, f_ref)
+    # error behaviour: forces before the faces were handed in
+    e2 = case.engine(precond_type=ptype)
+    from navierstokes_project_nm4pde_b200._lib import NsbError
+    with pytest.raises(NsbError):
+        e2.compute_forces()
+
+
 def test_bad_arguments_are_refused():
     """Error behaviour of the boundary: negative return codes + message, no exceptions across the ABI."""
     from navierstokes_project_nm4pde_b200._lib import NsbError

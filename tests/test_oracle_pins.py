@@ -434,3 +434,39 @@ def test_batched_gram_schmidt_matches_modified():
         sols.append(o.array("sol_owned", case.N).copy())
     assert abs(its[0] - its[1]) <= 2, its
     assert T.rel_l2(sols[1][: case.n_u], sols[0][: case.n_u]) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------ drag / lift
+@pytest.mark.parametrize("case_name", ["cyl2d", "cyl3d"])
+def test_compute_forces_closed_surface_identities(case_name):
+    """The oracle's restatement of NavierStokes::compute_forces (NavierStokes2D.cpp:752-859,
+    NavierStokes3D.cpp:744-840) against the divergence theorem on the closed obstacle boundary.  With the
+    reference's n = -(outward normal of the fluid cell) = outward normal of the HOLE:
+      pressure:  integral of -p n = -grad(p) |hole|            for a linear p            (2D and 3D)
+      viscous:   integral of nu (grad u) n = nu div(grad u) |hole|, = (2 nu |hole|, 0) for u = (y^2, 0)  (2D;
+                 P2 holds y^2 exactly)
+    and against the product's independent host implementation (nsh_boundary_forces) on a random field."""
+    import os, sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import helpers as T
+    from test_host_cpu import _hole_measure
+
+    case = T.Case(case_name)
+    o, d, dim = case.oracle(), case.dofs, case.dim
+    fc, fl = d.boundary_faces(3)
+    xi, w = T.gauss_simplex(dim - 1)
+    X, P = d.node_xyz, d.p_xyz
+    hole = _hole_measure(case.mesh, dim)
+    beta, gamma = 0.7, -1.3
+    p = 2.0 + beta * P[:, 0] + gamma * P[:, 1]
+    drag, lift = o.compute_forces(np.concatenate([np.zeros(d.n_u), p]), fc, fl, xi, w)
+    assert abs(drag + beta * hole) < 1e-10 and abs(lift + gamma * hole) < 1e-10
+    if dim == 2:
+        u = np.stack([X[:, 1] ** 2, np.zeros(len(X))], axis=1).ravel()
+        drag, lift = o.compute_forces(np.concatenate([u, np.zeros(d.n_p)]), fc, fl, xi, w)
+        assert abs(drag - 2.0 * case.nu * hole) < 1e-14 and abs(lift) < 1e-14
+    x = case.random_state()
+    a = o.compute_forces(x, fc, fl, xi, w, rho=1.0)
+    b = d.boundary_forces(x, 3, case.nu, 1.0)
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
