@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -272,12 +273,23 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     const int dim = H.dim, n2 = H.n2, nv1 = H.nv1;
     const int64_t nc = H.nc;
     H.nc_pad = (nc + 31) / 32 * 32;
+    // NSB_VERBOSE=1: where the (host-side, cold-path) setup time goes
+    const bool verbose = getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+      if (!verbose) return;
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[nsb setup rank %d] %-28s %8.2f s\n", H.rank, what, std::chrono::duration<double>(now - t_last).count());
+      t_last = now;
+    };
     // patterns (DoFTools::make_sparsity_pattern with the coupling table of NavierStokes2D.cpp:109-119)
     build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_nodes.data(), n2, H.n_nodes, H.n_nodes_owned, H.n_nodes, H.hFs);
     build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_p.data(), nv1, H.n_nodes, H.n_nodes, H.n_p, H.hBt);
     build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_nodes.data(), n2, H.n_p, H.n_p_owned, H.n_nodes, H.hB);
     build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_p.data(), nv1, H.n_p, H.n_p_owned, H.n_p, H.hMp);
+    phase("sparsity patterns");
     symbolic_product(H.hB, H.hBt, H.hS);
+    phase("symbolic Schur product");
     H.Fs.upload_pattern(H.hFs, 1);
     H.Bt.upload_pattern(H.hBt, dim);
     H.B.upload_pattern(H.hB, dim);
@@ -302,6 +314,7 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
       }
       H.d_mapF.upload(map);
     }
+    phase("uploads, scatter map");
     H.d_vcoords.upload(interleave32<double>(H.h_vcoords, nc, H.nc_pad, nv1 * dim, 0.0));
     H.d_cell_nodes.upload(interleave32<int>(H.h_cell_nodes, nc, H.nc_pad, n2, -1));
     H.d_cell_p.upload(interleave32<int>(H.h_cell_p, nc, H.nc_pad, nv1, 0));
@@ -326,6 +339,7 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
       if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
       if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
     }
+    phase("mesh arrays, vectors");
     stream_build_spmv(H);
     if (dim == 3) {
       sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, sell_lanes_for(H.hFs.n_rows), H.sellF);
@@ -333,8 +347,11 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
       H.d_xpad.zero();
     }
     H.sellF_dirty = true;
+    phase("SpMV formats (SELL, stream)");
     ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering);
+    phase("ILU schedule F");
     ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering);
+    phase("ILU schedule S");
     solver_alloc(H);
     NSB_CUDA(cudaDeviceSynchronize());
     H.finalized = true;

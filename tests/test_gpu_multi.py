@@ -59,7 +59,7 @@ def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
         e = prob.engine
         assert prob.transport == transport and e.stat("p2p") == (1.0 if transport == "p2p" else 0.0), prob.transport
         e.set_solution(prob.initial_condition())
-        its, sols = [], []
+        its, sols, forces = [], [], []
         t = 0.0
         for step in range(3):
             if case.variant == "conv":
@@ -74,9 +74,12 @@ def _worker(rank, world, port, case_name, ordering, orth, transport, out_q):
             its.append(e.solve_step()[0])
             gn, u, gp, p = prob.owned_solution()
             sols.append((gn.copy(), u.copy(), gp.copy(), p.copy()))
+            # drag / lift on the device, summed over the ranks (each rank integrates the faces of its own cells)
+            forces.append(e.compute_forces() if case.variant != "conv" else np.zeros(2))
         loc = prob.local
         out_q.put((rank, its, sols, loc["node_owner"] if rank == 0 else None, loc["p_owner"] if rank == 0 else None,
-                   (e.ilu_order(0), e.ilu_order(1), loc["node_gid"][: loc["n_nodes_owned"]], loc["p_gid"][: loc["n_p_owned"]])))
+                   (e.ilu_order(0), e.ilu_order(1), loc["node_gid"][: loc["n_nodes_owned"]], loc["p_gid"][: loc["n_p_owned"]]),
+                   forces))
     finally:
         dist.destroy_process_group()
 
@@ -162,6 +165,11 @@ def test_ranks_match_block_jacobi_oracle(case_name, ordering, orth, transport, w
             xe[: case.n_u].reshape(-1, dim)[gn] = u
             xe[case.n_u:][gp] = p
         assert all(r[1][step] == res[0][1][step] for r in res)
+        if case.variant != "conv":  # compute_forces across ranks == the oracle's face loop on the assembled global field
+            fc, fl = case.dofs.boundary_faces(3)
+            f_ref = o.compute_forces(xe, fc, fl, *T.gauss_simplex(dim - 1))
+            for r in res:
+                assert np.allclose(r[6][step], f_ref, rtol=1e-10, atol=1e-12 * np.abs(f_ref).max()), (step, r[0], r[6][step], f_ref)
         if res[0][1][step] == its_o:
             assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < 1e-8, step
         else:
