@@ -381,7 +381,9 @@ def run_gpu(args):
                            preconditioner=PRECOND[variant], deltat=run.dt,
                            quadrature="QGaussSimplex(3) / Witherden-Vincent",
                            ilu_ordering={0: "natural (reference replay)", 1: "multicolour (throughput mode)",
-                                         2: "block multicolour, natural order inside 32-row blocks (throughput mode)"}[args.ilu_ordering],
+                                         2: "block multicolour, natural order inside 32-row blocks (throughput mode)",
+                                         3: "subdomain ordering: parts solved out of shared memory, separators last "
+                                            "(throughput mode)"}[args.ilu_ordering],
                            orthogonalisation={0: "modified Gram-Schmidt (reference replay)",
                                               1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
@@ -448,9 +450,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default=None, choices=sorted(WORKLOADS),
                     help="mesh of the bounded CPU sample (cpu_baseline leg and --impl reference); default by core count")
-    ap.add_argument("--ilu-ordering", type=int, default=2, choices=[0, 1, 2],
-                    help="0: natural row order (reference replay), 1: multicolour ILU(0), 2: block multicolour ILU(0) "
-                         "(throughput mode, default)")
+    ap.add_argument("--ilu-ordering", type=int, default=2, choices=[0, 1, 2, 3],
+                    help="0: natural row order (reference replay), 1: multicolour ILU(0), 2: block multicolour ILU(0), "
+                         "3: subdomain-resident ILU(0) (throughput modes)")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
     args = ap.parse_args()

@@ -84,7 +84,10 @@ typedef struct nsb_params {
   int32_t sptrsv_kernel;   /* 0: default for this build, 1: level-scheduled launches, 2: chunked persistent */
   int32_t ilu_ordering;    /* 0: natural local row order (Ifpack in the reference; replay mode),
                               1: greedy multicolour ordering of the ILU(0) factors (throughput mode;
-                              a different but equally valid ILU(0), like a different mpirun -n P).
+                              a different but equally valid ILU(0), like a different mpirun -n P),
+                              2: block multicolour (blocks of 32 rows solved sequentially by a warp),
+                              3: subdomain ordering (compact parts whose interior rows are solved by one CTA
+                                 out of shared memory, separator rows last; csrc/kernels_sd.cu).
                               Must be set before nsb_finalize_setup. */
   int32_t orthogonalisation; /* 0: modified Gram-Schmidt exactly as SolverGMRES (replay mode),
                               1: batched classical Gram-Schmidt (throughput mode): all coefficients of one
@@ -223,6 +226,16 @@ int nsb_timer_mark(nsb_handle h, int which);
 int nsb_timer_elapsed_ms(nsb_handle h, double *ms);
 /* number of this library's kernel launches since the last call with reset != 0 */
 int64_t nsb_launch_count(nsb_handle h, int reset);
+
+/* CPU-only self check of the subdomain ILU ordering (ilu_ordering = 3) and its packed storage: builds the
+ * two-level ordering of the given (structurally symmetric, diagonal included) graph with parts of <= leaf
+ * rows, packs the factors as nsb_finalize_setup does, runs the triangular solves through a host emulation
+ * of the device kernels with synthetic values and bs right-hand sides, and returns the largest difference
+ * to plain substitution relative to max |y| (> 1e29: a structural invariant is violated).  stats[6]:
+ * parts, interior rows, separator colours, largest (interior + ring), most colours of a part, slot
+ * efficiency in per mille.  order_out[n] (may be NULL): factor row -> row.  Test infrastructure. */
+int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, const double *xyz, int32_t gdim,
+                       int32_t leaf, int32_t bs, double *rel_err, int32_t *stats, int32_t *order_out);
 
 /* ---- host prerequisites (cold path; replaces deal.II GridIn / DoFHandler in setup()) ---- */
 typedef struct nsh_mesh_s *nsh_mesh;

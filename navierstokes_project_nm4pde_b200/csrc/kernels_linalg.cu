@@ -729,6 +729,171 @@ static void block_multicolour_order(int n, const Csr &A, int n_owned_cols, std::
   if (colour_ptr.size() == 1) colour_ptr.push_back(0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Subdomain ordering (ilu_ordering = 3): a two-level ordering for triangular solves whose working
+// vector lives in SHARED MEMORY (kernels_sd.cu).
+//   1. The rows are cut into compact "parts" of <= leaf_max rows by recursive coordinate bisection of
+//      their support points.
+//   2. A row is a SEPARATOR row when it couples with a row of a lower-numbered part; all other rows
+//      are INTERIOR rows, and interior rows of different parts never couple.
+//   3. Factor order = [interior of part 0 | interior of part 1 | ... | separators]; inside a part and
+//      inside the separator set the rows are multicoloured (greedy, natural order) and sorted by
+//      (colour, row length): a colour is an independent set.
+// It is an exact ILU(0) of the same matrix in yet another elimination order.  In the forward solve
+// an interior row only reads rows of its own part, so one CTA solves a part start to finish with
+// the part's slice of the vector in shared memory -- no re-gathering of the vector from HBM between
+// colours (the point-multicolour sweeps moved 2.6x their algorithmic bytes, profiles/r01_traffic.json)
+// and ONE launch for ~85% of the rows instead of one per colour; the separator rows (~15%) follow as
+// colour sweeps over the global staging vector.  Backward: separators first, then the parts, which
+// also stage the separator values they couple with (their "ring").
+struct SdOrder {
+  std::vector<int> order;          // factor row -> matrix row
+  std::vector<int> part_ptr;       // [n_parts + 1] factor rows of each part's interior
+  std::vector<int> pcol_ptr, pcol; // per part: factor-row boundaries of its colours (pcol[pcol_ptr[p] ..]), first = part_ptr[p]
+  std::vector<int> sep_colour_ptr; // factor-row boundaries of the separator colours, first = n_interior, last = n
+};
+
+static void rcb_split(int *idx, int lo, int hi, const double *xyz, int gdim, int leaf_max,
+                      std::vector<std::pair<int, int>> &leaves)
+{
+  if (hi - lo <= leaf_max) {
+#pragma omp critical(nsb_rcb_leaves)
+    leaves.emplace_back(lo, hi);
+    return;
+  }
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int k = lo; k < hi; ++k)
+    for (int d = 0; d < gdim; ++d) {
+      const double v = xyz[size_t(idx[k]) * gdim + d];
+      mn[d] = std::min(mn[d], v); mx[d] = std::max(mx[d], v);
+    }
+  int dd = 0;
+  for (int d = 1; d < gdim; ++d)
+    if (mx[d] - mn[d] > mx[dd] - mn[dd]) dd = d;
+  const int mid = lo + (hi - lo) / 2;
+  std::nth_element(idx + lo, idx + mid, idx + hi, [&](int a, int b) {
+    const double xa = xyz[size_t(a) * gdim + dd], xb = xyz[size_t(b) * gdim + dd];
+    return xa < xb || (xa == xb && a < b);
+  });
+  [[maybe_unused]] const bool big = hi - lo > 200000;
+#pragma omp task default(shared) if (big)
+  rcb_split(idx, lo, mid, xyz, gdim, leaf_max, leaves);
+#pragma omp task default(shared) if (big)
+  rcb_split(idx, mid, hi, xyz, gdim, leaf_max, leaves);
+#pragma omp taskwait
+}
+
+static void subdomain_order(int n, const Csr &A, int n_owned_cols, const double *xyz, int gdim, int leaf_max, SdOrder &out)
+{
+  const int nc_lim = std::min(n, n_owned_cols);
+  // 1. parts
+  std::vector<int> idx(n), part(n, 0);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::vector<std::pair<int, int>> leaves;
+  if (xyz) {
+#pragma omp parallel
+#pragma omp single
+    rcb_split(idx.data(), 0, n, xyz, gdim, leaf_max, leaves);
+    std::sort(leaves.begin(), leaves.end());
+  } else // no geometry: runs of consecutive rows
+    for (int lo = 0; lo < n; lo += leaf_max) leaves.emplace_back(lo, std::min(n, lo + leaf_max));
+  const int np = int(leaves.size());
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int p = 0; p < np; ++p) {
+    std::sort(idx.begin() + leaves[p].first, idx.begin() + leaves[p].second); // natural order inside a part
+    for (int k = leaves[p].first; k < leaves[p].second; ++k) part[idx[k]] = p;
+  }
+  // 2. separators
+  std::vector<char> sep(n, 0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+      const int j = A.colind[k];
+      if (j < nc_lim && part[j] < part[i]) { sep[i] = 1; break; }
+    }
+  }
+  auto deg = [&](int i) { return A.rowptr[i + 1] - A.rowptr[i]; };
+  // 3. interiors: greedy colouring inside each part (interior rows of different parts never couple)
+  std::vector<int> colour(n, -1);
+  std::vector<std::vector<int>> pint(np), pcb(np); // interior rows in factor order, colour boundaries (local)
+#pragma omp parallel
+  {
+    std::vector<int> mark, rows;
+#pragma omp for schedule(dynamic, 16)
+    for (int p = 0; p < np; ++p) {
+      rows.clear();
+      int ncol = 0;
+      for (int k = leaves[p].first; k < leaves[p].second; ++k) {
+        const int i = idx[k];
+        if (sep[i]) continue;
+        mark.assign(ncol + 1, 0);
+        for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+          const int j = A.colind[e];
+          if (j < nc_lim && j != i && !sep[j] && colour[j] >= 0) mark[colour[j]] = 1; // j interior => same part
+        }
+        int c = 0;
+        while (mark[c]) ++c;
+        colour[i] = c;
+        if (c == ncol) ++ncol;
+        rows.push_back(i);
+      }
+      std::sort(rows.begin(), rows.end(), [&](int a, int b) {
+        if (colour[a] != colour[b]) return colour[a] < colour[b];
+        if (deg(a) != deg(b)) return deg(a) > deg(b);
+        return a < b;
+      });
+      pint[p] = rows;
+      pcb[p].assign(1, 0);
+      for (size_t t = 1; t <= rows.size(); ++t)
+        if (t == rows.size() || colour[rows[t]] != colour[rows[t - 1]]) pcb[p].push_back(int(t));
+      if (rows.empty()) pcb[p].push_back(0);
+    }
+  }
+  // 4. separators: greedy colouring of the induced subgraph, part after part
+  std::vector<int> seps;
+  {
+    std::vector<int> mark;
+    int ncol = 0;
+    for (int p = 0; p < np; ++p)
+      for (int k = leaves[p].first; k < leaves[p].second; ++k) {
+        const int i = idx[k];
+        if (!sep[i]) continue;
+        mark.assign(ncol + 1, 0);
+        for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+          const int j = A.colind[e];
+          if (j < nc_lim && j != i && sep[j] && colour[j] >= 0) mark[colour[j]] = 1;
+        }
+        int c = 0;
+        while (mark[c]) ++c;
+        colour[i] = c;
+        if (c == ncol) ++ncol;
+        seps.push_back(i);
+      }
+    std::stable_sort(seps.begin(), seps.end(), [&](int a, int b) { return colour[a] < colour[b]; });
+  }
+  // 5. assemble the order
+  out.order.clear();
+  out.order.reserve(n);
+  out.part_ptr.assign(1, 0);
+  out.pcol_ptr.assign(1, 0);
+  out.pcol.clear();
+  for (int p = 0; p < np; ++p) {
+    if (pint[p].empty()) continue; // a part made of separator rows only
+    const int base = int(out.order.size());
+    for (int b : pcb[p]) out.pcol.push_back(base + b);
+    out.pcol_ptr.push_back(int(out.pcol.size()));
+    out.order.insert(out.order.end(), pint[p].begin(), pint[p].end());
+    out.part_ptr.push_back(int(out.order.size()));
+  }
+  out.sep_colour_ptr.assign(1, int(out.order.size()));
+  for (size_t t = 0; t < seps.size(); ++t) {
+    out.order.push_back(seps[t]);
+    if (t + 1 == seps.size() || colour[seps[t + 1]] != colour[seps[t]]) out.sep_colour_ptr.push_back(int(out.order.size()));
+  }
+  if (out.sep_colour_ptr.size() == 1) out.sep_colour_ptr.push_back(int(out.order.size()));
+  if (int(out.order.size()) != n) throw StateError("subdomain ordering lost rows");
+}
+
 // rows per chunk of the multicolour ordering: NSB_ILU_CHUNK (rows), default 0 = one chunk.  Measured
 // at 19.9 M DoF (profiles/README.md): chunks of 0.8 / 1.25 / 2.5 M nodes make the F_s apply SLOWER
 // (3.3 / 2.9 / 2.2 ms against 1.68 ms unchunked) -- the 5x more, 5x smaller sweeps are latency-bound
@@ -742,20 +907,17 @@ static int ilu_chunk_rows(int bs_rhs)
 
 // ordering: 0 = natural local row order (what Ifpack does in the reference), 1 = multicolour.
 // The factor lives in the permuted index space: row k of the factor is row order[k] of A.
-void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering)
+// pattern of the factors in the permuted index space: row k = row order[k] of A, columns renumbered and
+// sorted, off-process columns dropped (Ifpack_LocalFilter); src[e]: position of entry e in A.
+static void permute_pattern(const Csr &A, const std::vector<int> &order, int n_owned_cols, std::vector<int> &rowptr,
+                            std::vector<int> &colind, std::vector<int> &src, std::vector<int> &diagpos)
 {
   const int n = A.n_rows;
-  ilu.n = n;
-  ilu.bs_rhs = bs_rhs;
-  ilu.h_order.clear();
-  std::vector<int> colour_ptr, blk_ptr, colour_blk;
-  if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu_chunk_rows(bs_rhs), ilu.h_order, colour_ptr);
-  else if (ordering == 2) block_multicolour_order(n, A, n_owned_cols, ilu.h_order, colour_ptr, blk_ptr, colour_blk);
-  else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
-  const std::vector<int> &order = ilu.h_order;
   std::vector<int> pos(n_owned_cols > n ? n_owned_cols : n, -1);
   for (int k = 0; k < n; ++k) pos[order[k]] = k;
-  std::vector<int> rowptr(n + 1, 0), colind, src, diagpos(n, 0);
+  rowptr.assign(n + 1, 0);
+  diagpos.assign(n, 0);
+  colind.clear(); src.clear();
   colind.reserve(A.colind.size());
   src.reserve(A.colind.size());
   std::vector<std::pair<int, int>> row;
@@ -777,6 +939,52 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
     while (colind[dp] != k) ++dp;
     diagpos[k] = dp;
   }
+}
+
+// CPU-only check of the subdomain ordering and its packed storage (tests/test_host_cpu.py)
+double sd_host_check(int n, const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                     const std::vector<int> &order, const std::vector<int> &part_ptr, const std::vector<int> &pcol_ptr,
+                     const std::vector<int> &pcol, const std::vector<int> &sep_colour_ptr, int bs, int *stats);
+double sd_debug_check(const Csr &A, const double *xyz, int gdim, int leaf, int bs, int *stats, int *order_out)
+{
+  SdOrder o;
+  subdomain_order(A.n_rows, A, A.n_rows, xyz, gdim, leaf, o);
+  std::vector<int> rowptr, colind, src, diagpos;
+  permute_pattern(A, o.order, A.n_rows, rowptr, colind, src, diagpos);
+  // an interior row may only couple with rows of its own part (forward) or separators (backward)
+  const int np = int(o.part_ptr.size()) - 1;
+  for (int p = 0; p < np; ++p)
+    for (int r = o.part_ptr[p]; r < o.part_ptr[p + 1]; ++r)
+      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+        const int c = colind[e];
+        if (!((c >= o.part_ptr[p] && c < o.part_ptr[p + 1]) || c >= o.part_ptr[np])) return 3e30;
+      }
+  if (order_out) std::copy(o.order.begin(), o.order.end(), order_out);
+  return sd_host_check(A.n_rows, rowptr, colind, diagpos, o.order, o.part_ptr, o.pcol_ptr, o.pcol, o.sep_colour_ptr, bs, stats);
+}
+
+static int sd_leaf_rows(int bs_rhs)
+{ // rows per part: the part's rows (+ ring) times bs_rhs doubles must leave room for two CTAs per SM
+  const char *e = getenv("NSB_SD_LEAF");
+  if (e && atoi(e) > 0) return atoi(e);
+  return bs_rhs == 3 ? 3072 : bs_rhs == 2 ? 4096 : 8192;
+}
+
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering, const double *xyz, int gdim)
+{
+  const int n = A.n_rows;
+  ilu.n = n;
+  ilu.bs_rhs = bs_rhs;
+  ilu.h_order.clear();
+  std::vector<int> colour_ptr, blk_ptr, colour_blk;
+  SdOrder sdo;
+  if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu_chunk_rows(bs_rhs), ilu.h_order, colour_ptr);
+  else if (ordering == 2) block_multicolour_order(n, A, n_owned_cols, ilu.h_order, colour_ptr, blk_ptr, colour_blk);
+  else if (ordering == 3) { subdomain_order(n, A, n_owned_cols, xyz, gdim, sd_leaf_rows(bs_rhs), sdo); ilu.h_order = sdo.order; }
+  else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
+  const std::vector<int> &order = ilu.h_order;
+  std::vector<int> rowptr, colind, src, diagpos;
+  permute_pattern(A, order, n_owned_cols, rowptr, colind, src, diagpos);
   ilu.nnz = int64_t(colind.size());
   ilu.rowptr.upload(rowptr);
   ilu.colind.upload(colind);
@@ -788,6 +996,17 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   std::vector<int> rows;
   ilu.stream = false;
   ilu.bsell = false;
+  ilu.sdmode = false;
+  if (ordering == 3) {
+    // numeric factorisation: exact dependency levels of the permuted pattern (interior colours of all parts
+    // in parallel, then the separator colours); triangular solves: kernels_sd.cu
+    level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);
+    ilu.lvl_rows_f.upload(rows);
+    ilu.lvl_ptr_b.assign(1, 0);
+    ilu.colour_ptr = sdo.sep_colour_ptr;
+    sd_build(ilu, rowptr, colind, diagpos, sdo.part_ptr, sdo.pcol_ptr, sdo.pcol, sdo.sep_colour_ptr);
+    return;
+  }
   if (ordering == 2) {
     // numeric factorisation: exact dependency levels of the permuted pattern (about colours x the
     // longest chain inside a block, ~200 launches once per time step); triangular solves: one launch
@@ -899,7 +1118,8 @@ void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val)
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());
-  if (ilu.bsell) bsell_fill(H, ilu);
+  if (ilu.sdmode) sd_fill(H, ilu);
+  else if (ilu.bsell) bsell_fill(H, ilu);
   else if (ilu.sell) {
     sell_fill(H, ilu.sellL, ilu.val.p);
     sell_fill(H, ilu.sellU, ilu.val.p);
@@ -1080,14 +1300,16 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
   const int nvals = ilu.n * ilu.bs_rhs;
   cudaStream_t s = H.stream;
   if (!ilu.graph_f) {
-    if (ilu.sell || ilu.bsell) ilu.io.alloc(2);
-    const size_t stage = ilu.sell ? size_t(4) * ilu.n : ilu.bsell ? size_t(bsell_stride(ilu.bs_rhs)) * ilu.n : size_t(nvals);
+    if (ilu.sell || ilu.bsell || ilu.sdmode) ilu.io.alloc(2);
+    const size_t stage = ilu.sdmode ? size_t(sd_stride(ilu.bs_rhs)) * ilu.n
+                         : ilu.sell ? size_t(4) * ilu.n : ilu.bsell ? size_t(bsell_stride(ilu.bs_rhs)) * ilu.n : size_t(nvals);
     NSB_CUDA(cudaMalloc((void **)&ilu.graph_x, sizeof(double) * stage));
     NSB_CUDA(cudaMemsetAsync(ilu.graph_x, 0, sizeof(double) * stage, s));
     cudaGraph_t g;
     const int64_t before = H.launches;
     NSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    if (ilu.bsell) bsell_trsv(H, ilu, ilu.graph_x, s);
+    if (ilu.sdmode) sd_trsv(H, ilu, ilu.graph_x, s);
+    else if (ilu.bsell) bsell_trsv(H, ilu, ilu.graph_x, s);
     else if (ilu.sell) sell_trsv(H, ilu, ilu.graph_x, s);
     else if (ilu.stream) stream_trsv(H, ilu, ilu.graph_x, s);
     else if (ilu.bs_rhs == 1) trsv_levels<1>(H, ilu, ilu.graph_x, s);
@@ -1098,10 +1320,10 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;
   }
-  if (ilu.sell || ilu.bsell) { // permutation in / out fused into the first forward and every backward launch
+  if (ilu.sell || ilu.bsell || ilu.sdmode) { // permutation in / out fused into the first forward and every backward launch
     sell_set_io(H, ilu, x, y);
     NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
-    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1);
+    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1) + (ilu.sdmode ? 2 : 0);
     return;
   }
   const unsigned pg = vgrid(nvals);

@@ -151,7 +151,7 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
     if (p->gmres_tmp < 3 || p->gmres_tmp > 60) throw ArgError("nsb_set_params: gmres_tmp must be in [3, 60]");
     if (p->orthogonalisation == 1 && p->gmres_tmp > 30)
       throw ArgError("nsb_set_params: orthogonalisation = 1 needs gmres_tmp <= 30 (the reference uses 30)");
-    if (p->ilu_ordering < 0 || p->ilu_ordering > 2) throw ArgError("nsb_set_params: ilu_ordering must be 0, 1 or 2");
+    if (p->ilu_ordering < 0 || p->ilu_ordering > 3) throw ArgError("nsb_set_params: ilu_ordering must be 0, 1, 2 or 3");
     if (p->orthogonalisation < 0 || p->orthogonalisation > 1)
       throw ArgError("nsb_set_params: orthogonalisation must be 0 or 1");
     if (H.finalized && p->ilu_ordering != H.prm.ilu_ordering)
@@ -348,9 +348,24 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     }
     H.sellF_dirty = true;
     phase("SpMV formats (SELL, stream)");
-    ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering);
+    std::vector<double> xyz_n, xyz_p; // support points of the P2 nodes / pressure vertices (subdomain ordering)
+    if (H.prm.ilu_ordering == 3) {
+      xyz_n.assign(size_t(H.n_nodes) * dim, 0.0);
+      xyz_p.assign(size_t(H.n_p) * dim, 0.0);
+      for (int64_t c = 0; c < nc; ++c) {
+        const double *X = &H.h_vcoords[c * nv1 * dim];
+        for (int a = 0; a < n2; ++a) {
+          const int node = H.h_cell_nodes[c * n2 + a];
+          const int va = a < nv1 ? a : kEdgeA[a - nv1], vb = a < nv1 ? a : kEdgeB[a - nv1];
+          for (int d = 0; d < dim; ++d) xyz_n[size_t(node) * dim + d] = 0.5 * (X[va * dim + d] + X[vb * dim + d]);
+        }
+        for (int v = 0; v < nv1; ++v)
+          for (int d = 0; d < dim; ++d) xyz_p[size_t(H.h_cell_p[c * nv1 + v]) * dim + d] = X[v * dim + d];
+      }
+    }
+    ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering, xyz_n.empty() ? nullptr : xyz_n.data(), dim);
     phase("ILU schedule F");
-    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering);
+    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering, xyz_p.empty() ? nullptr : xyz_p.data(), dim);
     phase("ILU schedule S");
     solver_alloc(H);
     NSB_CUDA(cudaDeviceSynchronize());
@@ -506,6 +521,24 @@ extern "C" int nsb_set_neumann_rhs(nsb_handle h, const double *rhs_u)
     h2d(H, H.d_neumann.p, rhs_u, sizeof(double) * H.nu_owned());
     H.have_neumann = true;
   });
+}
+
+// ---- CPU-only self check of the subdomain ILU storage (no GPU needed; tests/test_host_cpu.py) ------
+namespace nsb { double sd_debug_check(const Csr &A, const double *xyz, int gdim, int leaf, int bs, int *stats, int *order_out); }
+extern "C" int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, const double *xyz, int32_t gdim,
+                                  int32_t leaf, int32_t bs, double *rel_err, int32_t *stats, int32_t *order_out)
+{
+  try {
+    if (n <= 0 || !rowptr || !colind || !rel_err || bs < 1 || bs > 3) return NSB_ERR_ARG;
+    Csr A;
+    A.n_rows = A.n_cols = n;
+    A.rowptr.assign(rowptr, rowptr + n + 1);
+    A.colind.assign(colind, colind + rowptr[n]);
+    *rel_err = sd_debug_check(A, xyz, gdim, leaf, bs, stats, order_out);
+    return NSB_OK;
+  } catch (const std::exception &) {
+    return NSB_ERR_STATE;
+  }
 }
 
 // ---- drag / lift on the device (kernels_post.cu) ---------------------------------------------

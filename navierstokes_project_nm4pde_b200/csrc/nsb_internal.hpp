@@ -120,6 +120,30 @@ struct DevBsell {
   DevBuf<double> i_val;
 };
 
+// Subdomain-resident storage of the triangular factors (kernels_sd.cu, ilu_ordering = 3): the interior
+// rows of every part packed in processing order (values + 16-bit part-local columns), the separator
+// rows in SELL-32 (DevIlu::sellL / sellU).
+struct SdPart {
+  int row0, ni;          // first factor row / number of interior rows
+  int cs0, ncol;         // colour -> slice table of the direction this copy is for
+  int ring0, nring;      // backward solve: separator rows staged next to the part's own rows
+  int l_cs0, l_ncol, u_cs0, u_ncol; // build-time scratch
+};
+struct DevSdTri {
+  int n_slices = 0, max_local = 0;     // max_local: most (interior + ring) rows of any part
+  int64_t n_doubles = 0;
+  DevBuf<int4> slices;                 // x: stream offset / 8 doubles, y: steps, z: first local row, w: rows
+  DevBuf<int64_t> map_off;             // first fill-map slot of each slice
+  DevBuf<int> cslice, map, ring_rows;  // cslice: first slice of each (part, colour), +1 terminator per part
+  DevBuf<double> stream;
+};
+struct DevSd {
+  int n_parts = 0, n_interior = 0;
+  DevSdTri L, U;
+  DevBuf<SdPart> parts_f, parts_b;
+  std::vector<int> sep_colour_ptr;
+};
+
 // ILU(0) factors in Ifpack's storage convention (strict lower part = a_ij * dinv_j, strict upper
 // part scaled by dinv_i, inverse diagonal separate), on the owned-columns pattern, plus the
 // level schedules of the two triangular solves.
@@ -132,7 +156,8 @@ struct DevIlu {
   std::vector<int> h_order;
   DevBuf<double> val, dinv;
   // multicolour mode: split L / U factors and per-colour row blocks for the CSR-stream solves
-  bool stream = false, sell = false, bsell = false;
+  bool stream = false, sell = false, bsell = false, sdmode = false;
+  DevSd sd;                       // subdomain-resident mode (ilu_ordering = 3)
   DevSell sellL, sellU;
   DevBsell bL, bU;                // block multicolour mode (ilu_ordering = 2)
   DevBuf<int> blk_row;            // first factor row of each block, [n_blocks + 1]
@@ -355,7 +380,9 @@ void vec_multi_dot_dev(Handle &H, int n, const double *vv, const double *V, size
                        double *self_dev, bool allreduce = false);
 void vec_multi_axpy_dev(Handle &H, int n, double *vv, const double *V, size_t ld, int nv, const double *h_dev,
                         double *norm2_dev, bool allreduce = false);
-void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering);
+// xyz: support points of the rows [n_rows][gdim] (used by ordering 3; may be nullptr)
+void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering, const double *xyz = nullptr,
+               int gdim = 0);
 void ilu_factor(Handle &H, DevIlu &ilu, const double *A_val);
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y); // y = U^-1 D^-1 L^-1 x
 void spgemm_schur(Handle &H); // S = B diag(negDinv) Bt on the static pattern
@@ -386,6 +413,14 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
 void bsell_fill(Handle &H, DevIlu &ilu);
 int bsell_stride(int bs_rhs); // doubles per row of the staging vector
 void bsell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
+
+// ---------------------------------------------------------------- kernels_sd.cu
+void sd_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+              const std::vector<int> &part_ptr, const std::vector<int> &pcol_ptr, const std::vector<int> &pcol,
+              const std::vector<int> &sep_colour_ptr);
+void sd_fill(Handle &H, DevIlu &ilu);
+int sd_stride(int bs_rhs);
+void sd_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernels_post.cu
 void force_faces_set(Handle &H, int nf, const int *face_cell, const int *face_opp, int nq, const double *xi, const double *w);

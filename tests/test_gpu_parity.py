@@ -275,13 +275,17 @@ def _oracle_order(case, e):
     return ou, e.ilu_order(1)
 
 
-@pytest.mark.parametrize("ordering", [1, 2])
+@pytest.mark.parametrize("ordering", [1, 2, 3])
 @pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cube", "yosida"),
                                              ("cyl3d", "yosida"), ("box2d", "simple"), ("box3d", "ayosida")])
-def test_multicolour_ilu_mode(case_name, ptype, ordering):
+def test_multicolour_ilu_mode(case_name, ptype, ordering, monkeypatch):
     """Throughput modes (ilu_ordering = 1: point multicolour, 2: block multicolour with sequential
-    elimination inside 32-row blocks): ILU(0) of the permuted matrices.  Same checks as the replay
+    elimination inside 32-row blocks, 3: subdomain ordering -- parts solved by one CTA out of shared
+    memory, separator rows last; small parts here so that the test meshes have several of them): ILU(0)
+    of the permuted matrices.  Same checks as the replay
     mode, against the oracle factorising in the same ordering."""
+    if ordering == 3:
+        monkeypatch.setenv("NSB_SD_LEAF", "96")
     case = T.Case(case_name)
     o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=ordering)
     ou, op = _oracle_order(case, e)

@@ -235,3 +235,41 @@ def test_boundary_forces_exact_for_linear_fields(gen, dim):
         # side surface only: the closed-surface identity holds for the x and y components because the
         # missing caps have normals along z
         assert abs(drag + beta * hole) < 1e-10 and abs(lift + gamma * hole) < 1e-10
+
+
+@pytest.mark.parametrize("gen,dim,bs,leaf", [(lambda: HostMesh.cylinder3d(1, 3), 3, 3, 300), (lambda: HostMesh.cylinder2d(2), 2, 2, 200),
+                                             (lambda: HostMesh.cylinder3d(1, 3), 3, 1, 150), (lambda: HostMesh.cube(4), 3, 3, 64)])
+def test_subdomain_ilu_storage_cpu(gen, dim, bs, leaf):
+    """ilu_ordering = 3 without a GPU (nsb_debug_sd_check): the two-level subdomain ordering is a
+    permutation whose colours are independent sets and whose interior rows only couple with their own
+    part or with separator rows, and the packed per-part streams (16-bit local columns, rings) reproduce
+    plain forward / backward substitution through a host emulation of the device kernels."""
+    import ctypes as C
+
+    import scipy.sparse as sp
+
+    from navierstokes_project_nm4pde_b200 import _lib
+    from navierstokes_project_nm4pde_b200._lib import dptr, iptr
+
+    d = HostDofs(gen())
+    cd = d.cell_dofs(copy=False)
+    nv = dim + 1
+    if bs == 1:  # pressure graph squared ~ pattern of B D^-1 B^T
+        ids, n, xyz = cd[:, [v * (dim + 1) + dim for v in range(nv)]] - d.n_u, d.n_p, d.p_xyz
+    else:
+        ne = 3 if dim == 2 else 6
+        cols = [v * (dim + 1) for v in range(nv)] + [nv * (dim + 1) + e * dim for e in range(ne)]
+        ids, n, xyz = cd[:, cols] // dim, d.n_nodes, d.node_xyz
+    k = ids.shape[1]
+    A = sp.csr_matrix((np.ones(ids.size * k), (np.repeat(ids, k, axis=1).ravel(), np.tile(ids, (1, k)).ravel())), shape=(n, n))
+    if bs == 1:
+        A = (A @ A).tocsr()
+    A.sum_duplicates(); A.sort_indices()
+    rp, ci = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    err, stats, order = C.c_double(0), np.zeros(8, np.int32), np.zeros(n, np.int32)
+    xyz = np.ascontiguousarray(xyz)
+    rc = _lib.lib().nsb_debug_sd_check(n, iptr(rp), iptr(ci), dptr(xyz), dim, leaf, bs, C.byref(err), iptr(stats), iptr(order))
+    assert rc == 0
+    assert sorted(order.tolist()) == list(range(n))
+    assert err.value < 1e-12, err.value
+    assert stats[0] >= 2 and 0 < stats[1] < n and stats[3] <= 65535
