@@ -228,14 +228,17 @@ int nsb_timer_elapsed_ms(nsb_handle h, double *ms);
 int64_t nsb_launch_count(nsb_handle h, int reset);
 
 /* CPU-only self check of the subdomain ILU ordering (ilu_ordering = 3) and its packed storage: builds the
- * two-level ordering of the given (structurally symmetric, diagonal included) graph with parts of <= leaf
- * rows, packs the factors as nsb_finalize_setup does, runs the triangular solves through a host emulation
+ * multi-level ordering of the given (structurally symmetric, diagonal included) graph with parts of
+ * <= leaf_levels[l] rows on level l (three entries, 0 ends the list; no further level below min_active
+ * active rows), packs the factors as nsb_finalize_setup does, runs the triangular solves through a host emulation
  * of the device kernels with synthetic values and bs right-hand sides, and returns the largest difference
- * to plain substitution relative to max |y| (> 1e29: a structural invariant is violated).  stats[6]:
- * parts, interior rows, separator colours, largest (interior + ring), most colours of a part, slot
- * efficiency in per mille.  order_out[n] (may be NULL): factor row -> row.  Test infrastructure. */
+ * to plain substitution relative to max |y| (> 1e29: a structural invariant is violated).  stats[8]:
+ * parts, rows in parts, final separator colours, largest (rows + ring), most colours of a part, slot
+ * efficiency in per mille, levels, rows of level 1.  order_out[n] (may be NULL): factor row -> row.
+ * Test infrastructure. */
 int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, const double *xyz, int32_t gdim,
-                       int32_t leaf, int32_t bs, double *rel_err, int32_t *stats, int32_t *order_out);
+                       const int32_t *leaf_levels, int32_t min_active, int32_t bs, double *rel_err, int32_t *stats,
+                       int32_t *order_out);
 
 /* ---- host prerequisites (cold path; replaces deal.II GridIn / DoFHandler in setup()) ---- */
 typedef struct nsh_mesh_s *nsh_mesh;

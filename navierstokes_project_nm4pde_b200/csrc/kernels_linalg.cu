@@ -751,144 +751,161 @@ struct SdOrder {
   std::vector<int> part_ptr;       // [n_parts + 1] factor rows of each part's interior
   std::vector<int> pcol_ptr, pcol; // per part: factor-row boundaries of its colours (pcol[pcol_ptr[p] ..]), first = part_ptr[p]
   std::vector<int> sep_colour_ptr; // factor-row boundaries of the separator colours, first = n_interior, last = n
+  std::vector<int> level_part_ptr; // [n_levels + 1] parts of each level
 };
 
-static void rcb_split(int *idx, int lo, int hi, const double *xyz, int gdim, int leaf_max,
-                      std::vector<std::pair<int, int>> &leaves)
+// recursive coordinate bisection of idx[lo, hi) into k leaves of (nearly) equal size
+static void rcb_split(int *idx, int lo, int hi, const double *xyz, int gdim, int k, std::vector<std::pair<int, int>> &leaves)
 {
-  if (hi - lo <= leaf_max) {
+  if (k <= 1 || hi - lo <= 1) {
 #pragma omp critical(nsb_rcb_leaves)
     leaves.emplace_back(lo, hi);
     return;
   }
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-  for (int k = lo; k < hi; ++k)
+  for (int t = lo; t < hi; ++t)
     for (int d = 0; d < gdim; ++d) {
-      const double v = xyz[size_t(idx[k]) * gdim + d];
+      const double v = xyz[size_t(idx[t]) * gdim + d];
       mn[d] = std::min(mn[d], v); mx[d] = std::max(mx[d], v);
     }
   int dd = 0;
   for (int d = 1; d < gdim; ++d)
     if (mx[d] - mn[d] > mx[dd] - mn[dd]) dd = d;
-  const int mid = lo + (hi - lo) / 2;
+  const int k1 = k / 2;
+  const int mid = lo + int(int64_t(hi - lo) * k1 / k);
   std::nth_element(idx + lo, idx + mid, idx + hi, [&](int a, int b) {
     const double xa = xyz[size_t(a) * gdim + dd], xb = xyz[size_t(b) * gdim + dd];
     return xa < xb || (xa == xb && a < b);
   });
   [[maybe_unused]] const bool big = hi - lo > 200000;
 #pragma omp task default(shared) if (big)
-  rcb_split(idx, lo, mid, xyz, gdim, leaf_max, leaves);
+  rcb_split(idx, lo, mid, xyz, gdim, k1, leaves);
 #pragma omp task default(shared) if (big)
-  rcb_split(idx, mid, hi, xyz, gdim, leaf_max, leaves);
+  rcb_split(idx, mid, hi, xyz, gdim, k - k1, leaves);
 #pragma omp taskwait
 }
 
-static void subdomain_order(int n, const Csr &A, int n_owned_cols, const double *xyz, int gdim, int leaf_max, SdOrder &out)
+// Multi-level: the separator rows of level l are the active rows of level l + 1 and are cut into parts
+// again (they form sheets between the parts of level l, so their own separators are nearly 1D and few);
+// what is left after the last level is multicoloured globally.  Parts of one level never couple; a part
+// of level l couples with rows of earlier levels (forward solve: its "lower ring") and of later levels
+// (backward solve: its "upper ring").
+static void subdomain_order(int n, const Csr &A, int n_owned_cols, const double *xyz, int gdim, const std::vector<int> &leaf_max,
+                            int min_active, SdOrder &out)
 {
   const int nc_lim = std::min(n, n_owned_cols);
-  // 1. parts
-  std::vector<int> idx(n), part(n, 0);
-  for (int i = 0; i < n; ++i) idx[i] = i;
-  std::vector<std::pair<int, int>> leaves;
-  if (xyz) {
-#pragma omp parallel
-#pragma omp single
-    rcb_split(idx.data(), 0, n, xyz, gdim, leaf_max, leaves);
-    std::sort(leaves.begin(), leaves.end());
-  } else // no geometry: runs of consecutive rows
-    for (int lo = 0; lo < n; lo += leaf_max) leaves.emplace_back(lo, std::min(n, lo + leaf_max));
-  const int np = int(leaves.size());
-#pragma omp parallel for schedule(dynamic, 16)
-  for (int p = 0; p < np; ++p) {
-    std::sort(idx.begin() + leaves[p].first, idx.begin() + leaves[p].second); // natural order inside a part
-    for (int k = leaves[p].first; k < leaves[p].second; ++k) part[idx[k]] = p;
-  }
-  // 2. separators
-  std::vector<char> sep(n, 0);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < n; ++i) {
-    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-      const int j = A.colind[k];
-      if (j < nc_lim && part[j] < part[i]) { sep[i] = 1; break; }
-    }
-  }
   auto deg = [&](int i) { return A.rowptr[i + 1] - A.rowptr[i]; };
-  // 3. interiors: greedy colouring inside each part (interior rows of different parts never couple)
-  std::vector<int> colour(n, -1);
-  std::vector<std::vector<int>> pint(np), pcb(np); // interior rows in factor order, colour boundaries (local)
-#pragma omp parallel
-  {
-    std::vector<int> mark, rows;
-#pragma omp for schedule(dynamic, 16)
-    for (int p = 0; p < np; ++p) {
-      rows.clear();
-      int ncol = 0;
-      for (int k = leaves[p].first; k < leaves[p].second; ++k) {
-        const int i = idx[k];
-        if (sep[i]) continue;
-        mark.assign(ncol + 1, 0);
-        for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
-          const int j = A.colind[e];
-          if (j < nc_lim && j != i && !sep[j] && colour[j] >= 0) mark[colour[j]] = 1; // j interior => same part
-        }
-        int c = 0;
-        while (mark[c]) ++c;
-        colour[i] = c;
-        if (c == ncol) ++ncol;
-        rows.push_back(i);
-      }
-      std::sort(rows.begin(), rows.end(), [&](int a, int b) {
-        if (colour[a] != colour[b]) return colour[a] < colour[b];
-        if (deg(a) != deg(b)) return deg(a) > deg(b);
-        return a < b;
-      });
-      pint[p] = rows;
-      pcb[p].assign(1, 0);
-      for (size_t t = 1; t <= rows.size(); ++t)
-        if (t == rows.size() || colour[rows[t]] != colour[rows[t - 1]]) pcb[p].push_back(int(t));
-      if (rows.empty()) pcb[p].push_back(0);
-    }
-  }
-  // 4. separators: greedy colouring of the induced subgraph, part after part
-  std::vector<int> seps;
-  {
-    std::vector<int> mark;
-    int ncol = 0;
-    for (int p = 0; p < np; ++p)
-      for (int k = leaves[p].first; k < leaves[p].second; ++k) {
-        const int i = idx[k];
-        if (!sep[i]) continue;
-        mark.assign(ncol + 1, 0);
-        for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
-          const int j = A.colind[e];
-          if (j < nc_lim && j != i && sep[j] && colour[j] >= 0) mark[colour[j]] = 1;
-        }
-        int c = 0;
-        while (mark[c]) ++c;
-        colour[i] = c;
-        if (c == ncol) ++ncol;
-        seps.push_back(i);
-      }
-    std::stable_sort(seps.begin(), seps.end(), [&](int a, int b) { return colour[a] < colour[b]; });
-  }
-  // 5. assemble the order
+  std::vector<int> active(n), part(n, -1), colour(n, -1);
+  std::vector<char> is_active(n, 1), sep(n, 0);
+  for (int i = 0; i < n; ++i) active[i] = i;
   out.order.clear();
   out.order.reserve(n);
   out.part_ptr.assign(1, 0);
   out.pcol_ptr.assign(1, 0);
   out.pcol.clear();
-  for (int p = 0; p < np; ++p) {
-    if (pint[p].empty()) continue; // a part made of separator rows only
-    const int base = int(out.order.size());
-    for (int b : pcb[p]) out.pcol.push_back(base + b);
-    out.pcol_ptr.push_back(int(out.pcol.size()));
-    out.order.insert(out.order.end(), pint[p].begin(), pint[p].end());
-    out.part_ptr.push_back(int(out.order.size()));
+  out.level_part_ptr.assign(1, 0);
+  for (size_t level = 0; level < leaf_max.size(); ++level) {
+    const int na = int(active.size());
+    if (na == 0 || (level > 0 && na < min_active)) break;
+    // 1. parts of the active rows
+    std::vector<int> &idx = active;
+    std::vector<std::pair<int, int>> leaves;
+    if (xyz) {
+#pragma omp parallel
+#pragma omp single
+      rcb_split(idx.data(), 0, na, xyz, gdim, (na + leaf_max[level] - 1) / leaf_max[level], leaves);
+      std::sort(leaves.begin(), leaves.end());
+    } else // no geometry: runs of consecutive rows
+      for (int lo = 0; lo < na; lo += leaf_max[level]) leaves.emplace_back(lo, std::min(na, lo + leaf_max[level]));
+    const int np = int(leaves.size());
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int p = 0; p < np; ++p) {
+      std::sort(idx.begin() + leaves[p].first, idx.begin() + leaves[p].second); // natural order inside a part
+      for (int k = leaves[p].first; k < leaves[p].second; ++k) part[idx[k]] = p;
+    }
+    // 2. separators: active rows coupling with an active row of a lower-numbered part
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < na; ++t) {
+      const int i = idx[t];
+      sep[i] = 0;
+      for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+        const int j = A.colind[k];
+        if (j < nc_lim && is_active[j] && part[j] < part[i]) { sep[i] = 1; break; }
+      }
+    }
+    // 3. interiors: greedy colouring inside each part (interior rows of different parts never couple)
+    std::vector<std::vector<int>> pint(np), pcb(np); // interior rows in factor order, colour boundaries (local)
+#pragma omp parallel
+    {
+      std::vector<int> mark, rows;
+#pragma omp for schedule(dynamic, 16)
+      for (int p = 0; p < np; ++p) {
+        rows.clear();
+        int ncol = 0;
+        for (int k = leaves[p].first; k < leaves[p].second; ++k) {
+          const int i = idx[k];
+          if (sep[i]) continue;
+          mark.assign(ncol + 1, 0);
+          for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+            const int j = A.colind[e];
+            // an active interior neighbour lies in the same part; its colour is only set by this thread
+            if (j < nc_lim && j != i && is_active[j] && !sep[j] && part[j] == p && colour[j] >= 0) mark[colour[j]] = 1;
+          }
+          int c = 0;
+          while (mark[c]) ++c;
+          colour[i] = c;
+          if (c == ncol) ++ncol;
+          rows.push_back(i);
+        }
+        std::sort(rows.begin(), rows.end(), [&](int a, int b) {
+          if (colour[a] != colour[b]) return colour[a] < colour[b];
+          if (deg(a) != deg(b)) return deg(a) > deg(b);
+          return a < b;
+        });
+        pint[p] = rows;
+        pcb[p].assign(1, 0);
+        for (size_t t = 1; t <= rows.size(); ++t)
+          if (t == rows.size() || colour[rows[t]] != colour[rows[t - 1]]) pcb[p].push_back(int(t));
+      }
+    }
+    // 4. append the parts of this level; the separators stay active
+    std::vector<int> next;
+    for (int p = 0; p < np; ++p) {
+      for (int k = leaves[p].first; k < leaves[p].second; ++k)
+        if (sep[idx[k]]) next.push_back(idx[k]);
+      if (pint[p].empty()) continue; // a part made of separator rows only
+      const int base = int(out.order.size());
+      for (int b : pcb[p]) out.pcol.push_back(base + b);
+      out.pcol_ptr.push_back(int(out.pcol.size()));
+      out.order.insert(out.order.end(), pint[p].begin(), pint[p].end());
+      out.part_ptr.push_back(int(out.order.size()));
+      for (int i : pint[p]) is_active[i] = 0;
+    }
+    out.level_part_ptr.push_back(int(out.part_ptr.size()) - 1);
+    active.swap(next);
+  }
+  // 5. what is left: greedy colouring of the induced subgraph, colour by colour
+  {
+    std::vector<int> mark;
+    int ncol = 0;
+    for (int i : active) colour[i] = -1;
+    for (int i : active) {
+      mark.assign(ncol + 1, 0);
+      for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+        const int j = A.colind[e];
+        if (j < nc_lim && j != i && is_active[j] && colour[j] >= 0) mark[colour[j]] = 1;
+      }
+      int c = 0;
+      while (mark[c]) ++c;
+      colour[i] = c;
+      if (c == ncol) ++ncol;
+    }
+    std::stable_sort(active.begin(), active.end(), [&](int a, int b) { return colour[a] < colour[b]; });
   }
   out.sep_colour_ptr.assign(1, int(out.order.size()));
-  for (size_t t = 0; t < seps.size(); ++t) {
-    out.order.push_back(seps[t]);
-    if (t + 1 == seps.size() || colour[seps[t + 1]] != colour[seps[t]]) out.sep_colour_ptr.push_back(int(out.order.size()));
+  for (size_t t = 0; t < active.size(); ++t) {
+    out.order.push_back(active[t]);
+    if (t + 1 == active.size() || colour[active[t + 1]] != colour[active[t]]) out.sep_colour_ptr.push_back(int(out.order.size()));
   }
   if (out.sep_colour_ptr.size() == 1) out.sep_colour_ptr.push_back(int(out.order.size()));
   if (int(out.order.size()) != n) throw StateError("subdomain ordering lost rows");
@@ -944,30 +961,54 @@ static void permute_pattern(const Csr &A, const std::vector<int> &order, int n_o
 // CPU-only check of the subdomain ordering and its packed storage (tests/test_host_cpu.py)
 double sd_host_check(int n, const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
                      const std::vector<int> &order, const std::vector<int> &part_ptr, const std::vector<int> &pcol_ptr,
-                     const std::vector<int> &pcol, const std::vector<int> &sep_colour_ptr, int bs, int *stats);
-double sd_debug_check(const Csr &A, const double *xyz, int gdim, int leaf, int bs, int *stats, int *order_out)
+                     const std::vector<int> &pcol, const std::vector<int> &sep_colour_ptr, const std::vector<int> &level_part_ptr,
+                     int bs, int *stats);
+double sd_debug_check(const Csr &A, const double *xyz, int gdim, const int *leaf_levels, int min_active, int bs, int *stats,
+                      int *order_out)
 {
   SdOrder o;
-  subdomain_order(A.n_rows, A, A.n_rows, xyz, gdim, leaf, o);
+  std::vector<int> leaves;
+  for (int k = 0; k < 3 && leaf_levels[k] > 0; ++k) leaves.push_back(leaf_levels[k]);
+  subdomain_order(A.n_rows, A, A.n_rows, xyz, gdim, leaves, min_active, o);
   std::vector<int> rowptr, colind, src, diagpos;
   permute_pattern(A, o.order, A.n_rows, rowptr, colind, src, diagpos);
-  // an interior row may only couple with rows of its own part (forward) or separators (backward)
+  // a part's rows may only couple with their own part and with rows of OTHER levels
   const int np = int(o.part_ptr.size()) - 1;
-  for (int p = 0; p < np; ++p)
-    for (int r = o.part_ptr[p]; r < o.part_ptr[p + 1]; ++r)
-      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
-        const int c = colind[e];
-        if (!((c >= o.part_ptr[p] && c < o.part_ptr[p + 1]) || c >= o.part_ptr[np])) return 3e30;
-      }
+  for (size_t l = 0; l + 1 < o.level_part_ptr.size(); ++l) {
+    const int lv0 = o.part_ptr[o.level_part_ptr[l]], lv1 = o.part_ptr[o.level_part_ptr[l + 1]];
+    for (int p = o.level_part_ptr[l]; p < o.level_part_ptr[l + 1]; ++p)
+      for (int r = o.part_ptr[p]; r < o.part_ptr[p + 1]; ++r)
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+          const int c = colind[e];
+          if (!((c >= o.part_ptr[p] && c < o.part_ptr[p + 1]) || c < lv0 || c >= lv1)) return 3e30;
+        }
+  }
+  (void)np;
   if (order_out) std::copy(o.order.begin(), o.order.end(), order_out);
-  return sd_host_check(A.n_rows, rowptr, colind, diagpos, o.order, o.part_ptr, o.pcol_ptr, o.pcol, o.sep_colour_ptr, bs, stats);
+  return sd_host_check(A.n_rows, rowptr, colind, diagpos, o.order, o.part_ptr, o.pcol_ptr, o.pcol, o.sep_colour_ptr,
+                       o.level_part_ptr, bs, stats);
 }
 
-static int sd_leaf_rows(int bs_rhs)
-{ // rows per part: the part's rows (+ ring) times bs_rhs doubles must leave room for two CTAs per SM
-  const char *e = getenv("NSB_SD_LEAF");
-  if (e && atoi(e) > 0) return atoi(e);
-  return bs_rhs == 3 ? 3072 : bs_rhs == 2 ? 4096 : 8192;
+static std::vector<int> sd_leaf_rows(int bs_rhs)
+{ // rows per part and level: a part's rows + ring times bs_rhs doubles should leave room for two CTAs per SM.
+  // NSB_SD_LEAF = "l1[,l2[,l3]]" overrides (one entry = one level).
+  std::vector<int> v;
+  if (const char *e = getenv("NSB_SD_LEAF")) {
+    for (const char *p = e; *p;) {
+      const int x = atoi(p);
+      if (x > 0) v.push_back(x);
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+    if (!v.empty()) return v;
+  }
+  const int l1 = bs_rhs == 3 ? 3072 : bs_rhs == 2 ? 4096 : 8192;
+  return {l1, l1 / 4, l1 / 4};
+}
+static int sd_min_active()
+{ // fewer active rows than this: no further level, colour them
+  const char *e = getenv("NSB_SD_MIN_ACTIVE");
+  return e ? atoi(e) : 20000;
 }
 
 void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering, const double *xyz, int gdim)
@@ -980,7 +1021,18 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   SdOrder sdo;
   if (ordering == 1) multicolour_order(n, A, n_owned_cols, ilu_chunk_rows(bs_rhs), ilu.h_order, colour_ptr);
   else if (ordering == 2) block_multicolour_order(n, A, n_owned_cols, ilu.h_order, colour_ptr, blk_ptr, colour_blk);
-  else if (ordering == 3) { subdomain_order(n, A, n_owned_cols, xyz, gdim, sd_leaf_rows(bs_rhs), sdo); ilu.h_order = sdo.order; }
+  else if (ordering == 3) {
+    // parts as large as shared memory allows: shrink the leaves until every part (rows + ring) fits
+    std::vector<int> leaves = sd_leaf_rows(bs_rhs);
+    for (int attempt = 0;; ++attempt) {
+      subdomain_order(n, A, n_owned_cols, xyz, gdim, leaves, sd_min_active(), sdo);
+      std::vector<int> rp, ci, sr, dp;
+      permute_pattern(A, sdo.order, n_owned_cols, rp, ci, sr, dp);
+      if (sd_smem_needed(rp, ci, dp, sdo.part_ptr, bs_rhs) <= size_t(220) * 1024 || attempt == 6) break;
+      for (int &l : leaves) l = std::max(32, l * 3 / 4);
+    }
+    ilu.h_order = sdo.order;
+  }
   else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
   const std::vector<int> &order = ilu.h_order;
   std::vector<int> rowptr, colind, src, diagpos;
@@ -1004,7 +1056,7 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
     ilu.lvl_rows_f.upload(rows);
     ilu.lvl_ptr_b.assign(1, 0);
     ilu.colour_ptr = sdo.sep_colour_ptr;
-    sd_build(ilu, rowptr, colind, diagpos, sdo.part_ptr, sdo.pcol_ptr, sdo.pcol, sdo.sep_colour_ptr);
+    sd_build(ilu, rowptr, colind, diagpos, sdo.part_ptr, sdo.pcol_ptr, sdo.pcol, sdo.sep_colour_ptr, sdo.level_part_ptr);
     return;
   }
   if (ordering == 2) {
@@ -1323,7 +1375,7 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
   if (ilu.sell || ilu.bsell || ilu.sdmode) { // permutation in / out fused into the first forward and every backward launch
     sell_set_io(H, ilu, x, y);
     NSB_CUDA(cudaGraphLaunch(ilu.graph_f, s));
-    H.launches += 2 * (int64_t(ilu.colour_ptr.size()) - 1) + (ilu.sdmode ? 2 : 0);
+    H.launches += ilu.sdmode ? int64_t(sd_launches(ilu)) : 2 * (int64_t(ilu.colour_ptr.size()) - 1);
     return;
   }
   const unsigned pg = vgrid(nvals);

@@ -524,9 +524,13 @@ extern "C" int nsb_set_neumann_rhs(nsb_handle h, const double *rhs_u)
 }
 
 // ---- CPU-only self check of the subdomain ILU storage (no GPU needed; tests/test_host_cpu.py) ------
-namespace nsb { double sd_debug_check(const Csr &A, const double *xyz, int gdim, int leaf, int bs, int *stats, int *order_out); }
+namespace nsb {
+double sd_debug_check(const Csr &A, const double *xyz, int gdim, const int *leaf_levels, int min_active, int bs, int *stats,
+                      int *order_out);
+}
 extern "C" int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, const double *xyz, int32_t gdim,
-                                  int32_t leaf, int32_t bs, double *rel_err, int32_t *stats, int32_t *order_out)
+                                  const int32_t *leaf_levels, int32_t min_active, int32_t bs, double *rel_err, int32_t *stats,
+                                  int32_t *order_out)
 {
   try {
     if (n <= 0 || !rowptr || !colind || !rel_err || bs < 1 || bs > 3) return NSB_ERR_ARG;
@@ -534,7 +538,8 @@ extern "C" int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_
     A.n_rows = A.n_cols = n;
     A.rowptr.assign(rowptr, rowptr + n + 1);
     A.colind.assign(colind, colind + rowptr[n]);
-    *rel_err = sd_debug_check(A, xyz, gdim, leaf, bs, stats, order_out);
+    if (!leaf_levels) return NSB_ERR_ARG;
+    *rel_err = sd_debug_check(A, xyz, gdim, leaf_levels, min_active, bs, stats, order_out);
     return NSB_OK;
   } catch (const std::exception &) {
     return NSB_ERR_STATE;

@@ -120,21 +120,22 @@ struct DevBsell {
   DevBuf<double> i_val;
 };
 
-// Subdomain-resident storage of the triangular factors (kernels_sd.cu, ilu_ordering = 3): the interior
-// rows of every part packed in processing order (values + 16-bit part-local columns), the separator
-// rows in SELL-32 (DevIlu::sellL / sellU).
+// Subdomain-resident storage of the triangular factors (kernels_sd.cu, ilu_ordering = 3): the rows of
+// every part packed in processing order as a sequence of ROUNDS (one bulk copy each), the rows left
+// after the last level in SELL-32 (DevIlu::sellL / sellU).
 struct SdPart {
-  int row0, ni;          // first factor row / number of interior rows
-  int cs0, ncol;         // colour -> slice table of the direction this copy is for
-  int ring0, nring;      // backward solve: separator rows staged next to the part's own rows
-  int l_cs0, l_ncol, u_cs0, u_ncol; // build-time scratch
+  int row0, ni;          // first factor row / number of rows of the part
+  int round0, nrounds;   // rounds of the direction this copy is for
+  int ring0, nring;      // rows of other levels staged next to the part's own rows (its "ring")
 };
 struct DevSdTri {
-  int n_slices = 0, max_local = 0;     // max_local: most (interior + ring) rows of any part
+  int n_rounds = 0, n_slices = 0;
   int64_t n_doubles = 0;
-  DevBuf<int4> slices;                 // x: stream offset / 8 doubles, y: steps, z: first local row, w: rows
+  DevBuf<int4> rounds;                 // x: stream offset / 16 B, y: bytes, z: slices, w: colour
+  DevBuf<int2> fill_slices;            // x: offset of the slice's values in the stream (doubles), y: steps
   DevBuf<int64_t> map_off;             // first fill-map slot of each slice
-  DevBuf<int> cslice, map, ring_rows;  // cslice: first slice of each (part, colour), +1 terminator per part
+  DevBuf<int> map, ring_rows;
+  DevBuf<int2> dfill;                  // backward only: (stream offset in doubles, factor row) of every dinv slot
   DevBuf<double> stream;
 };
 struct DevSd {
@@ -142,6 +143,9 @@ struct DevSd {
   DevSdTri L, U;
   DevBuf<SdPart> parts_f, parts_b;
   std::vector<int> sep_colour_ptr;
+  std::vector<int> level_part_ptr;               // parts of each level
+  std::vector<int> level_local_f, level_local_b; // largest (rows + ring) of a level's parts, per direction
+  std::vector<int> level_rounds_f, level_rounds_b; // most rounds of a level's parts, per direction
 };
 
 // ILU(0) factors in Ifpack's storage convention (strict lower part = a_ij * dinv_j, strict upper
@@ -417,9 +421,12 @@ void bsell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
 // ---------------------------------------------------------------- kernels_sd.cu
 void sd_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
               const std::vector<int> &part_ptr, const std::vector<int> &pcol_ptr, const std::vector<int> &pcol,
-              const std::vector<int> &sep_colour_ptr);
+              const std::vector<int> &sep_colour_ptr, const std::vector<int> &level_part_ptr);
+size_t sd_smem_needed(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                      const std::vector<int> &part_ptr, int bs);
 void sd_fill(Handle &H, DevIlu &ilu);
 int sd_stride(int bs_rhs);
+int sd_launches(const DevIlu &ilu); // kernel launches of one triangular solve pair
 void sd_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernels_post.cu

@@ -284,8 +284,9 @@ def test_multicolour_ilu_mode(case_name, ptype, ordering, monkeypatch):
     memory, separator rows last; small parts here so that the test meshes have several of them): ILU(0)
     of the permuted matrices.  Same checks as the replay
     mode, against the oracle factorising in the same ordering."""
-    if ordering == 3:
-        monkeypatch.setenv("NSB_SD_LEAF", "96")
+    if ordering == 3:  # three levels of small parts, no lower bound on the rows of a level
+        monkeypatch.setenv("NSB_SD_LEAF", "96,32,32")
+        monkeypatch.setenv("NSB_SD_MIN_ACTIVE", "0")
     case = T.Case(case_name)
     o, e = case.oracle(), case.engine(precond_type=ptype, ilu_ordering=ordering)
     ou, op = _oracle_order(case, e)

@@ -240,10 +240,11 @@ def test_boundary_forces_exact_for_linear_fields(gen, dim):
 @pytest.mark.parametrize("gen,dim,bs,leaf", [(lambda: HostMesh.cylinder3d(1, 3), 3, 3, 300), (lambda: HostMesh.cylinder2d(2), 2, 2, 200),
                                              (lambda: HostMesh.cylinder3d(1, 3), 3, 1, 150), (lambda: HostMesh.cube(4), 3, 3, 64)])
 def test_subdomain_ilu_storage_cpu(gen, dim, bs, leaf):
-    """ilu_ordering = 3 without a GPU (nsb_debug_sd_check): the two-level subdomain ordering is a
-    permutation whose colours are independent sets and whose interior rows only couple with their own
-    part or with separator rows, and the packed per-part streams (16-bit local columns, rings) reproduce
-    plain forward / backward substitution through a host emulation of the device kernels."""
+    """ilu_ordering = 3 without a GPU (nsb_debug_sd_check): the multi-level subdomain ordering is a
+    permutation whose colours are independent sets and whose part rows only couple with their own part
+    or with rows of other levels, and the packed per-part streams (rounds, slice headers, 16-bit local
+    columns, rings) reproduce plain forward / backward substitution through a host emulation of the
+    device kernels."""
     import ctypes as C
 
     import scipy.sparse as sp
@@ -268,8 +269,12 @@ def test_subdomain_ilu_storage_cpu(gen, dim, bs, leaf):
     rp, ci = A.indptr.astype(np.int32), A.indices.astype(np.int32)
     err, stats, order = C.c_double(0), np.zeros(8, np.int32), np.zeros(n, np.int32)
     xyz = np.ascontiguousarray(xyz)
-    rc = _lib.lib().nsb_debug_sd_check(n, iptr(rp), iptr(ci), dptr(xyz), dim, leaf, bs, C.byref(err), iptr(stats), iptr(order))
-    assert rc == 0
-    assert sorted(order.tolist()) == list(range(n))
-    assert err.value < 1e-12, err.value
-    assert stats[0] >= 2 and 0 < stats[1] < n and stats[3] <= 65535
+    for levels in ([leaf, 0, 0], [leaf, leaf // 3, leaf // 3]):  # one level; three levels (separators cut into parts again)
+        lv = np.array(levels, np.int32)
+        rc = _lib.lib().nsb_debug_sd_check(n, iptr(rp), iptr(ci), dptr(xyz), dim, iptr(lv), 0, bs, C.byref(err), iptr(stats),
+                                           iptr(order))
+        assert rc == 0
+        assert sorted(order.tolist()) == list(range(n))
+        assert err.value < 1e-12, err.value
+        assert stats[0] >= 2 and 0 < stats[1] <= n and stats[3] <= 65535
+        assert stats[6] == (1 if levels[1] == 0 else 3) or stats[1] == n
