@@ -105,14 +105,15 @@ struct DevSell {
 
 // Block-sequential storage of one triangular factor in the block multicolour ordering (kernels_sell.cu,
 // "bsell"): a block is <= 32 consecutive factor rows solved by one warp.  Entries that couple with other
-// blocks ("ext", all of them final when the block's colour is swept) are packed block by block, sorted
-// by row, padded to a multiple of 32 per block, and reduced per row by a segmented warp scan; entries
+// blocks ("ext", all of them final when the block's colour is swept) are stored in four passes of eight
+// rows with four lanes per row (rows sorted by their ext count) and reduced per row by two shuffles; entries
 // inside the block ("int") are packed row by row and resolved sequentially by shuffle broadcast.
 struct DevBsell {
   int n_blocks = 0, max_int = 0;    // max_int: most intra-block entries of any block
   int64_t n_ext = 0, n_int = 0;
   DevBuf<int> e_ptr, e_col, e_map;  // e_ptr[b]: first ext slot of block b (multiple of 32)
-  DevBuf<unsigned char> e_row;      // local row (0..31) of each ext slot
+  DevBuf<unsigned> e_len;           // steps of the four ext passes of each block (one byte each)
+  DevBuf<unsigned char> e_prow;     // [n_blocks][32] local row of each (pass, slot)
   DevBuf<double> e_val;
   DevBuf<int> i_ptr, i_map;         // i_ptr[b]: first intra entry of block b
   DevBuf<unsigned short> i_off;     // [n_blocks][33] offsets of each local row inside the block's entries
