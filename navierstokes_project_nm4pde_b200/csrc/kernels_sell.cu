@@ -318,9 +318,9 @@ constexpr int kBW = 4; // warps (= blocks of rows) per CTA
 
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
 
-static size_t bsell_warp_bytes(int bs, int max_int)
-{ // acc[32*bs] doubles | ival[max_int] doubles | ioff[33] ushort (72 B) | icol[max_int] bytes
-  const size_t b = size_t(32) * bs * 8 + size_t(max_int) * 8 + 72 + size_t(max_int);
+static size_t bsell_warp_bytes(int bs, int max_int, int max_nx)
+{ // acc[32*bs] doubles | xs[max_nx*bs] doubles | ival[max_int] doubles | ioff[33] ushort (72 B) | icol[max_int] bytes
+  const size_t b = size_t(32) * bs * 8 + size_t(max_nx) * bs * 8 + size_t(max_int) * 8 + 72 + size_t(max_int);
   return (b + 15) & ~size_t(15);
 }
 
@@ -345,13 +345,14 @@ template <int BS, int DIR>
 __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
                                                        const int *__restrict__ e_ptr, const unsigned *__restrict__ e_len,
                                                        const unsigned char *__restrict__ e_prow,
-                                                       const int *__restrict__ e_col, const double *__restrict__ e_val,
-                                                       const int *__restrict__ i_ptr,
+                                                       const unsigned short *__restrict__ e_lix,
+                                                       const double *__restrict__ e_val, const int *__restrict__ x_ptr,
+                                                       const int *__restrict__ x_ids, const int *__restrict__ i_ptr,
                                                        const unsigned short *__restrict__ i_off,
                                                        const unsigned char *__restrict__ i_col,
                                                        const double *__restrict__ i_val, double *yp,
                                                        const double *__restrict__ dinv, const int *__restrict__ order,
-                                                       const TrsvIo *__restrict__ io, int max_int, int warp_bytes)
+                                                       const TrsvIo *__restrict__ io, int max_int, int max_nx, int warp_bytes)
 {
   constexpr int PS = BS == 3 ? 4 : BS;
   constexpr unsigned FULL = 0xffffffffu;
@@ -361,7 +362,8 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   if (b >= b1) return; // the whole warp leaves; there is no block-wide barrier below
   unsigned char *base = bsell_smem + size_t(warp) * warp_bytes;
   double *acc = reinterpret_cast<double *>(base);
-  double *sval = acc + 32 * BS;
+  double *xs = acc + 32 * BS;          // the block's distinct outside rows, staged once
+  double *sval = xs + size_t(max_nx) * BS;
   unsigned short *soff = reinterpret_cast<unsigned short *>(sval + max_int);
   unsigned char *scol = reinterpret_cast<unsigned char *>(soff) + 72;
   const int r0 = blk_row[b], nr = blk_row[b + 1] - r0;
@@ -384,16 +386,28 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
       for (int d = 0; d < BS; ++d) res[d] = yi[d] * di;
     }
   }
+  // ---- stage the distinct rows of other blocks this block couples with (each is used ~3 times): ONE
+  // round trip to HBM / L2 for all of them instead of one per step of the passes below
+  {
+    const int xb = x_ptr[b], nx = x_ptr[b + 1] - xb;
+    for (int k = lane; k < nx; k += 32) {
+      double x[BS];
+      bsell_gather<BS>(yp, x_ids[xb + k], x);
+#pragma unroll
+      for (int d = 0; d < BS; ++d) xs[k * BS + d] = x[d];
+    }
+  }
   const int ib = i_ptr[b], ni = i_ptr[b + 1] - ib;
   for (int k = lane; k < ni; k += 32) {
     sval[k] = __ldcs(i_val + ib + k);
     scol[k] = i_col[ib + k];
   }
   for (int k = lane; k < 33; k += 32) soff[k] = i_off[size_t(b) * 33 + k];
+  __syncwarp();
   // ---- entries coupling with other blocks: four passes of eight rows, four lanes per row
   {
     const unsigned lens = e_len[b];
-    const int *cp = e_col + e_ptr[b] + lane;
+    const unsigned short *cp = e_lix + e_ptr[b] + lane;
     const double *vp = e_val + e_ptr[b] + lane;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -401,12 +415,10 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
       double a[BS];
 #pragma unroll
       for (int d = 0; d < BS; ++d) a[d] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
       for (int k = 0; k < len; ++k) {
-        const int c = __ldcs(cp + k * 32);
+        const double *x = xs + int(__ldcs(cp + k * 32)) * BS;
         const double v = __ldcs(vp + k * 32);
-        double x[BS];
-        bsell_gather<BS>(yp, c, x);
 #pragma unroll
         for (int d = 0; d < BS; ++d) a[d] += v * x[d];
       }
@@ -462,10 +474,14 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
 }
 
 static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<int> &colind,
-                            const std::vector<int> &diagpos, const std::vector<int> &blk_ptr, bool lower, DevBsell &out)
+                            const std::vector<int> &diagpos, const std::vector<int> &blk_ptr,
+                            const std::vector<int> &colour_blk, bool lower, DevBsell &out)
 {
   const int nb = int(blk_ptr.size()) - 1;
-  std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), e_col, e_map, i_map;
+  std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), e_map, i_map, x_ptr(nb + 1, 0), x_ids;
+  std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
+  std::vector<int> xloc(rowptr.size() - 1, -1); // factor row -> position in the current block's list
+  int max_nx = 0;
   std::vector<unsigned> e_len(nb, 0u);
   std::vector<unsigned char> e_prow(size_t(nb) * 32, 0), i_col;
   std::vector<unsigned short> i_off(size_t(nb) * 33, 0);
@@ -487,6 +503,15 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
         if (!intra) ext[r - r0].push_back(e);
       }
     }
+    // distinct outside rows in first-use order
+    for (int lr = 0; lr < 32; ++lr)
+      for (int e : ext[lr]) {
+        const int c = colind[e];
+        if (xloc[c] < 0) { xloc[c] = int(x_ids.size()) - x_ptr[b]; x_ids.push_back(c); }
+      }
+    x_ptr[b + 1] = int(x_ids.size());
+    if (x_ptr[b + 1] - x_ptr[b] > 65535) throw StateError("bsell: more than 65535 outside rows in a block");
+    max_nx = std::max(max_nx, x_ptr[b + 1] - x_ptr[b]);
     // passes of eight rows with similar numbers of outside entries; local rows >= r1 - r0 are empty fillers
     for (int lr = 0; lr < 32; ++lr) srt[lr] = lr;
     std::stable_sort(srt.begin(), srt.end(), [&](int x, int y) { return ext[x].size() > ext[y].size(); });
@@ -501,15 +526,15 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
       e_map.resize(base + size_t(len) * 32, -1);
       for (int l = 0; l < 32; ++l) {
         const std::vector<int> &ex = ext[srt[q * 8 + l / 4]];
-        const int pad_col = ex.empty() ? 0 : colind[ex[0]]; // a final, valid row of the staging vector (value 0)
         for (int k = 0; k < len; ++k) {
           const size_t o = base + size_t(k) * 32 + l;
           const size_t e = size_t(k) * 4 + (l & 3);
-          if (e < ex.size()) { e_col[o] = colind[ex[e]]; e_map[o] = ex[e]; }
-          else e_col[o] = pad_col;
+          if (e < ex.size()) { e_col[o] = (unsigned short)xloc[colind[ex[e]]]; e_map[o] = ex[e]; }
+          else e_col[o] = 0; // padding: value 0 times the first staged row (len > 0 implies the list is not empty)
         }
       }
     }
+    for (int k = x_ptr[b]; k < x_ptr[b + 1]; ++k) xloc[x_ids[k]] = -1;
     for (int t = 0; t < 32; ++t) e_prow[size_t(b) * 32 + t] = (unsigned char)srt[t];
     e_len[b] = lens;
     if (e_col.size() > size_t(0x7fffffff)) throw StateError("bsell: more than 2^31 slots");
@@ -535,9 +560,21 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   }
   out.n_blocks = nb;
   out.max_int = max_int;
+  out.max_nx = max_nx;
+  // shared memory is sized per launch (= per block colour) by the largest list of that colour
+  out.col_max_nx.assign(colour_blk.size() > 0 ? colour_blk.size() - 1 : 0, 0);
+  for (size_t c = 0; c + 1 < colour_blk.size(); ++c)
+    for (int b = colour_blk[c]; b < colour_blk[c + 1]; ++b)
+      out.col_max_nx[c] = std::max(out.col_max_nx[c], x_ptr[b + 1] - x_ptr[b]);
+  if (getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 0)
+    std::fprintf(stderr, "[nsb bsell %s] blocks %d, ext slots %zu (%.1f per row), intra %zu, outside rows %zu (max %d per block), max intra %d\n",
+                 lower ? "L" : "U", nb, e_col.size(), double(e_col.size()) / std::max(1, blk_ptr[nb]), i_col.size(), x_ids.size(),
+                 max_nx, max_int);
+  out.x_ptr.upload(x_ptr);
+  out.x_ids.upload(x_ids.empty() ? std::vector<int>(1, 0) : x_ids);
   out.n_ext = int64_t(e_col.size());
   out.n_int = int64_t(i_col.size());
-  out.e_ptr.upload(e_ptr); out.e_col.upload(e_col); out.e_map.upload(e_map);
+  out.e_ptr.upload(e_ptr); out.e_lix.upload(e_col); out.e_map.upload(e_map);
   out.e_len.upload(e_len); out.e_prow.upload(e_prow);
   out.e_val.alloc(e_col.size());
   out.i_ptr.upload(i_ptr); out.i_map.upload(i_map); out.i_off.upload(i_off); out.i_col.upload(i_col);
@@ -549,8 +586,26 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
 {
   ilu.blk_row.upload(blk_ptr);
   ilu.colour_blk = colour_blk;
-  bsell_build_one(rowptr, colind, diagpos, blk_ptr, true, ilu.bL);
-  bsell_build_one(rowptr, colind, diagpos, blk_ptr, false, ilu.bU);
+  bsell_build_one(rowptr, colind, diagpos, blk_ptr, colour_blk, true, ilu.bL);
+  bsell_build_one(rowptr, colind, diagpos, blk_ptr, colour_blk, false, ilu.bU);
+  // a colour whose blocks stage long lists may need more than the default 48 KB of dynamic shared memory
+  // (set here: the launches happen inside a stream capture)
+  const size_t need = kBW * std::max(bsell_warp_bytes(ilu.bs_rhs, ilu.bL.max_int, ilu.bL.max_nx),
+                                     bsell_warp_bytes(ilu.bs_rhs, ilu.bU.max_int, ilu.bU.max_nx));
+  if (need > size_t(227) * 1024) throw StateError("bsell: a block does not fit shared memory");
+  if (need > size_t(48) * 1024) {
+    const int lim = int(need);
+    if (ilu.bs_rhs == 3) {
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    } else if (ilu.bs_rhs == 2) {
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    } else {
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    }
+  }
 }
 
 void bsell_fill(Handle &H, DevIlu &ilu)
@@ -567,13 +622,15 @@ void bsell_fill(Handle &H, DevIlu &ilu)
 }
 
 template <int BS, int DIR>
-static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, int b0, int b1, double *yp, const TrsvIo *io)
+static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, int colour, int b0, int b1, double *yp,
+                         const TrsvIo *io)
 {
-  const size_t wb = bsell_warp_bytes(BS, B.max_int);
+  const int max_nx = B.col_max_nx[colour];
+  const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
-  k_bsell<BS, DIR><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_col.p, B.e_val.p,
-                                                     B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, yp, ilu.dinv.p,
-                                                     ilu.order.p, io, B.max_int, int(wb));
+  k_bsell<BS, DIR><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_val.p,
+                                                     B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, yp,
+                                                     ilu.dinv.p, ilu.order.p, io, B.max_int, max_nx, int(wb));
 }
 
 template <int BS>
@@ -584,13 +641,13 @@ static void bsell_trsv_t(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
   for (int c = 0; c < nc; ++c) {
     const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
     if (b <= a) continue;
-    launch_bsell<BS, 0>(s, ilu, ilu.bL, a, b, yp, io);
+    launch_bsell<BS, 0>(s, ilu, ilu.bL, c, a, b, yp, io);
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
     if (b <= a) continue;
-    launch_bsell<BS, 1>(s, ilu, ilu.bU, a, b, yp, io);
+    launch_bsell<BS, 1>(s, ilu, ilu.bU, c, a, b, yp, io);
     H.launches++;
   }
 }

@@ -110,8 +110,12 @@ struct DevSell {
 // inside the block ("int") are packed row by row and resolved sequentially by shuffle broadcast.
 struct DevBsell {
   int n_blocks = 0, max_int = 0;    // max_int: most intra-block entries of any block
+  int max_nx = 0;                   // most distinct outside rows of any block
+  std::vector<int> col_max_nx;      // the same per block colour (sizes the shared memory of that colour's launch)
   int64_t n_ext = 0, n_int = 0;
-  DevBuf<int> e_ptr, e_col, e_map;  // e_ptr[b]: first ext slot of block b (multiple of 32)
+  DevBuf<int> e_ptr, e_map;         // e_ptr[b]: first ext slot of block b (multiple of 32)
+  DevBuf<unsigned short> e_lix;     // per ext slot: index into the block's list of distinct outside rows
+  DevBuf<int> x_ptr, x_ids;         // per block: its distinct outside rows (factor rows), staged into shared memory once
   DevBuf<unsigned> e_len;           // steps of the four ext passes of each block (one byte each)
   DevBuf<unsigned char> e_prow;     // [n_blocks][32] local row of each (pass, slot)
   DevBuf<double> e_val;
