@@ -315,6 +315,13 @@ void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
 // `order`) and the inverse permutation into the backward sweep, as in k_sell3.
 // ------------------------------------------------------------------------------------------------
 constexpr int kBW = 4; // warps (= blocks of rows) per CTA
+// outside rows of a block staged in shared memory; the (few) others are gathered from global.  NSB_BSELL_XCAP overrides
+// (0: no staging at all).
+static int bsell_xcap()
+{
+  const char *e = getenv("NSB_BSELL_XCAP");
+  return e ? std::max(0, atoi(e)) : 128;
+}
 
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
 
@@ -350,7 +357,8 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
                                                        const int *__restrict__ x_ids, const int *__restrict__ i_ptr,
                                                        const unsigned short *__restrict__ i_off,
                                                        const unsigned char *__restrict__ i_col,
-                                                       const double *__restrict__ i_val, double *yp,
+                                                       const double *__restrict__ i_val,
+                                                       const unsigned *__restrict__ i_mask, double *yp,
                                                        const double *__restrict__ dinv, const int *__restrict__ order,
                                                        const TrsvIo *__restrict__ io, int max_int, int max_nx, int warp_bytes)
 {
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   // ---- stage the distinct rows of other blocks this block couples with (each is used ~3 times): ONE
   // round trip to HBM / L2 for all of them instead of one per step of the passes below
   {
-    const int xb = x_ptr[b], nx = x_ptr[b + 1] - xb;
+    const int xb = x_ptr[b], nx = min(x_ptr[b + 1] - xb, max_nx);
     for (int k = lane; k < nx; k += 32) {
       double x[BS];
       bsell_gather<BS>(yp, x_ids[xb + k], x);
@@ -417,10 +425,18 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
       for (int d = 0; d < BS; ++d) a[d] = 0.0;
 #pragma unroll 4
       for (int k = 0; k < len; ++k) {
-        const double *x = xs + int(__ldcs(cp + k * 32)) * BS;
+        const int li = int(__ldcs(cp + k * 32));
         const double v = __ldcs(vp + k * 32);
+        if (li < max_nx) { // staged
+          const double *x = xs + li * BS;
 #pragma unroll
-        for (int d = 0; d < BS; ++d) a[d] += v * x[d];
+          for (int d = 0; d < BS; ++d) a[d] += v * x[d];
+        } else { // beyond the staging capacity (large blocks only): straight from the staging vector
+          double x[BS];
+          bsell_gather<BS>(yp, x_ids[x_ptr[b] + li], x);
+#pragma unroll
+          for (int d = 0; d < BS; ++d) a[d] += v * x[d];
+        }
       }
       cp += len * 32;
       vp += len * 32;
@@ -444,10 +460,11 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
     const int pe = valid ? int(soff[lane + 1]) : 0;
     int cc = p < pe ? int(scol[p]) : 255;
     double cv = p < pe ? sval[p] : 0.0;
-#pragma unroll 4
-    for (int step = 0; step < 32; ++step) {
-      const int r = DIR == 0 ? step : 31 - step;
-      if (r >= nr) continue; // warp-uniform
+    // only rows that some later row of the block couples with need to be handed on
+    unsigned m = i_mask[b];
+    while (m) { // warp-uniform
+      const int r = DIR == 0 ? __ffs(int(m)) - 1 : 31 - __clz(int(m));
+      m &= ~(1u << r);
       double y[BS];
 #pragma unroll
       for (int d = 0; d < BS; ++d) y[d] = __shfl_sync(FULL, res[d], r);
@@ -482,7 +499,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
   std::vector<int> xloc(rowptr.size() - 1, -1); // factor row -> position in the current block's list
   int max_nx = 0;
-  std::vector<unsigned> e_len(nb, 0u);
+  std::vector<unsigned> e_len(nb, 0u), i_mask(nb, 0u); // i_mask: local rows that occur as an intra-block column
   std::vector<unsigned char> e_prow(size_t(nb) * 32, 0), i_col;
   std::vector<unsigned short> i_off(size_t(nb) * 33, 0);
   e_col.reserve(colind.size() / 2);
@@ -552,7 +569,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
         if (intra) tmp.emplace_back(c - r0, e);
       }
       if (!lower) std::reverse(tmp.begin(), tmp.end()); // descending columns for the backward sweep
-      for (auto &ce : tmp) { i_col.push_back((unsigned char)ce.first); i_map.push_back(ce.second); }
+      for (auto &ce : tmp) { i_col.push_back((unsigned char)ce.first); i_map.push_back(ce.second); i_mask[b] |= 1u << ce.first; }
     }
     i_off[size_t(b) * 33 + 32] = (unsigned short)(i_col.size() - ibase);
     max_int = std::max(max_int, int(i_col.size() - ibase));
@@ -565,7 +582,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   out.col_max_nx.assign(colour_blk.size() > 0 ? colour_blk.size() - 1 : 0, 0);
   for (size_t c = 0; c + 1 < colour_blk.size(); ++c)
     for (int b = colour_blk[c]; b < colour_blk[c + 1]; ++b)
-      out.col_max_nx[c] = std::max(out.col_max_nx[c], x_ptr[b + 1] - x_ptr[b]);
+      out.col_max_nx[c] = std::min(bsell_xcap(), std::max(out.col_max_nx[c], x_ptr[b + 1] - x_ptr[b]));
   if (getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 0)
     std::fprintf(stderr, "[nsb bsell %s] blocks %d, ext slots %zu (%.1f per row), intra %zu, outside rows %zu (max %d per block), max intra %d\n",
                  lower ? "L" : "U", nb, e_col.size(), double(e_col.size()) / std::max(1, blk_ptr[nb]), i_col.size(), x_ids.size(),
@@ -578,6 +595,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   out.e_len.upload(e_len); out.e_prow.upload(e_prow);
   out.e_val.alloc(e_col.size());
   out.i_ptr.upload(i_ptr); out.i_map.upload(i_map); out.i_off.upload(i_off); out.i_col.upload(i_col);
+  out.i_mask.upload(i_mask);
   out.i_val.alloc(i_col.size());
 }
 
@@ -590,8 +608,8 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
   bsell_build_one(rowptr, colind, diagpos, blk_ptr, colour_blk, false, ilu.bU);
   // a colour whose blocks stage long lists may need more than the default 48 KB of dynamic shared memory
   // (set here: the launches happen inside a stream capture)
-  const size_t need = kBW * std::max(bsell_warp_bytes(ilu.bs_rhs, ilu.bL.max_int, ilu.bL.max_nx),
-                                     bsell_warp_bytes(ilu.bs_rhs, ilu.bU.max_int, ilu.bU.max_nx));
+  const size_t need = kBW * std::max(bsell_warp_bytes(ilu.bs_rhs, ilu.bL.max_int, std::min(bsell_xcap(), ilu.bL.max_nx)),
+                                     bsell_warp_bytes(ilu.bs_rhs, ilu.bU.max_int, std::min(bsell_xcap(), ilu.bU.max_nx)));
   if (need > size_t(227) * 1024) throw StateError("bsell: a block does not fit shared memory");
   if (need > size_t(48) * 1024) {
     const int lim = int(need);
@@ -629,7 +647,7 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
   const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
   k_bsell<BS, DIR><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_val.p,
-                                                     B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, yp,
+                                                     B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp,
                                                      ilu.dinv.p, ilu.order.p, io, B.max_int, max_nx, int(wb));
 }
 

@@ -121,6 +121,7 @@ struct DevBsell {
   DevBuf<double> e_val;
   DevBuf<int> i_ptr, i_map;         // i_ptr[b]: first intra entry of block b
   DevBuf<unsigned short> i_off;     // [n_blocks][33] offsets of each local row inside the block's entries
+  DevBuf<unsigned> i_mask;          // per block: local rows that occur as a column of an intra entry
   DevBuf<unsigned char> i_col;      // local column (0..31); ascending per row (L), descending (U)
   DevBuf<double> i_val;
 };
