@@ -63,6 +63,8 @@ WORKLOADS = {"cyl3d-20M": ("3d", (8, 40)), "cyl3d-16M": ("3d", (8, 32)), "cyl3d-
              "cyl3d-30k": ("3d", (1, 3)), "cyl2d-2M": ("2d", (28,)), "cyl2d-160k": ("2d", (8,)), "cyl2d-3k": ("2d", (1,))}
 DELTAT = {"3d": 2e-4, "2d": 0.01}          # main3D.cpp:38, main2D.cpp:22
 PRECOND = {"3d": "yosida", "2d": "asimple"}  # NavierStokes3D.cpp:562, NavierStokes2D.cpp:547
+N_DOFS = {"cyl3d-20M": 19923035, "cyl3d-2M": 2059237, "cyl3d-500k": 530456}
+AUTO_BLOCK_MIN_DOFS = 8e6                   # --ilu-ordering -1: block multicolour ILU above this many DoF per GPU
 PREP_INNER_RTOL = 1e-4                      # inner tolerance of the two untimed start-up steps
 PREP_STEPS = 2
 
@@ -72,6 +74,12 @@ def make_mesh(workload):
 
     variant, a = WORKLOADS[workload]
     return (HostMesh.cylinder3d(*a) if variant == "3d" else HostMesh.cylinder2d(*a)), variant
+
+
+def HostDofsCount(mesh):
+    from navierstokes_project_nm4pde_b200 import HostDofs
+
+    return HostDofs(mesh).N
 
 
 def mesh_label(workload):
@@ -224,8 +232,13 @@ class GpuRun:
 
         self.torch = torch
         self.mesh, self.variant = make_mesh(workload)
+        if args.ilu_ordering < 0:  # automatic: by the DoFs one GPU holds
+            n_dofs = N_DOFS.get(workload) or HostDofsCount(self.mesh)
+            self.ilu_ordering = 2 if n_dofs / max(world, 1) >= AUTO_BLOCK_MIN_DOFS else 1
+        else:
+            self.ilu_ordering = args.ilu_ordering
         self.dt = DELTAT[self.variant]
-        kw = dict(T=1.0, deltat=self.dt, test_case=2, device=local_rank, ilu_ordering=args.ilu_ordering,
+        kw = dict(T=1.0, deltat=self.dt, test_case=2, device=local_rank, ilu_ordering=self.ilu_ordering,
                   orthogonalisation=args.orthogonalisation)
         if world > 1:
             from navierstokes_project_nm4pde_b200.distributed import DistributedNavierStokes
@@ -297,7 +310,7 @@ def run_gpu(args):
     run = GpuRun(args.workload, args, world, rank, local_rank, uid[0])
     e, prob = run.e, run.prob
     setup_s = time.perf_counter() - t_setup
-    log(f"setup done: {args.workload}, {run.mesh.n_cells} cells, {run.n_dofs} DoF, transport {getattr(prob, 'transport', 'none')}")
+    log(f"setup done: {args.workload}, {run.mesh.n_cells} cells, {run.n_dofs} DoF, ilu_ordering {run.ilu_ordering}, transport {getattr(prob, 'transport', 'none')}")
 
     barrier(); t0 = time.perf_counter()
     its_prep = run.prepare()
@@ -364,7 +377,7 @@ def run_gpu(args):
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f).get(dom, {})
-        if tj.get("workload") == args.workload and world == 1 and tj.get("ilu_ordering", args.ilu_ordering) == args.ilu_ordering:
+        if tj.get("workload") == args.workload and world == 1 and tj.get("ilu_ordering", run.ilu_ordering) == run.ilu_ordering:
             traffic = tj.get("dram_bytes_per_apply", tj.get("dram_bytes_per_launch"))
     except Exception:
         pass
@@ -383,7 +396,7 @@ def run_gpu(args):
                            ilu_ordering={0: "natural (reference replay)", 1: "multicolour (throughput mode)",
                                          2: "block multicolour, natural order inside 32-row blocks (throughput mode)",
                                          3: "subdomain ordering: parts solved out of shared memory, separators last "
-                                            "(throughput mode)"}[args.ilu_ordering],
+                                            "(throughput mode)"}[run.ilu_ordering],
                            orthogonalisation={0: "modified Gram-Schmidt (reference replay)",
                                               1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
@@ -450,9 +463,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default=None, choices=sorted(WORKLOADS),
                     help="mesh of the bounded CPU sample (cpu_baseline leg and --impl reference); default by core count")
-    ap.add_argument("--ilu-ordering", type=int, default=2, choices=[0, 1, 2, 3],
+    ap.add_argument("--ilu-ordering", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
                     help="0: natural row order (reference replay), 1: multicolour ILU(0), 2: block multicolour ILU(0), "
-                         "3: subdomain-resident ILU(0) (throughput modes)")
+                         "3: subdomain-resident ILU(0) (throughput modes); -1 (default): 2 above 8 M DoF per GPU, else 1 "
+                         "(measured: the block sweeps need large colours, profiles/README.md)")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
     args = ap.parse_args()

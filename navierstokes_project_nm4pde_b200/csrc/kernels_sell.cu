@@ -320,7 +320,7 @@ constexpr int kBW = 4; // warps (= blocks of rows) per CTA
 static int bsell_xcap()
 {
   const char *e = getenv("NSB_BSELL_XCAP");
-  return e ? std::max(0, atoi(e)) : 128;
+  return e ? std::max(0, atoi(e)) : 1024;
 }
 
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
@@ -348,11 +348,12 @@ __device__ __forceinline__ void bsell_gather(const double *yp, int c, double (&x
 
 // DIR 0: forward substitution  y = x - L y          (unit diagonal, Ifpack: L scaled by dinv_j)
 // DIR 1: backward substitution y = y * dinv - U y   (Ifpack: U scaled by dinv_i), also stored to io->y
-template <int BS, int DIR>
+template <int BS, int DIR, bool STAGE>
 __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
                                                        const int *__restrict__ e_ptr, const unsigned *__restrict__ e_len,
                                                        const unsigned char *__restrict__ e_prow,
                                                        const unsigned short *__restrict__ e_lix,
+                                                       const int *__restrict__ e_col,
                                                        const double *__restrict__ e_val, const int *__restrict__ x_ptr,
                                                        const int *__restrict__ x_ids, const int *__restrict__ i_ptr,
                                                        const unsigned short *__restrict__ i_off,
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   }
   // ---- stage the distinct rows of other blocks this block couples with (each is used ~3 times): ONE
   // round trip to HBM / L2 for all of them instead of one per step of the passes below
-  {
+  if (STAGE) {
     const int xb = x_ptr[b], nx = min(x_ptr[b + 1] - xb, max_nx);
     for (int k = lane; k < nx; k += 32) {
       double x[BS];
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   {
     const unsigned lens = e_len[b];
     const unsigned short *cp = e_lix + e_ptr[b] + lane;
+    const int *gp = e_col + e_ptr[b] + lane;
     const double *vp = e_val + e_ptr[b] + lane;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -425,20 +427,21 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
       for (int d = 0; d < BS; ++d) a[d] = 0.0;
 #pragma unroll 4
       for (int k = 0; k < len; ++k) {
-        const int li = int(__ldcs(cp + k * 32));
         const double v = __ldcs(vp + k * 32);
-        if (li < max_nx) { // staged
+        const int li = STAGE ? int(__ldcs(cp + k * 32)) : 0;
+        if (STAGE && li < max_nx) { // staged
           const double *x = xs + li * BS;
 #pragma unroll
           for (int d = 0; d < BS; ++d) a[d] += v * x[d];
-        } else { // beyond the staging capacity (large blocks only): straight from the staging vector
+        } else { // not staged (or beyond the staging capacity): straight from the staging vector
           double x[BS];
-          bsell_gather<BS>(yp, x_ids[x_ptr[b] + li], x);
+          bsell_gather<BS>(yp, __ldcs(gp + k * 32), x);
 #pragma unroll
           for (int d = 0; d < BS; ++d) a[d] += v * x[d];
         }
       }
       cp += len * 32;
+      gp += len * 32;
       vp += len * 32;
 #pragma unroll
       for (int o = 1; o < 4; o <<= 1)
@@ -460,11 +463,12 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
     const int pe = valid ? int(soff[lane + 1]) : 0;
     int cc = p < pe ? int(scol[p]) : 255;
     double cv = p < pe ? sval[p] : 0.0;
-    // only rows that some later row of the block couples with need to be handed on
-    unsigned m = i_mask[b];
-    while (m) { // warp-uniform
-      const int r = DIR == 0 ? __ffs(int(m)) - 1 : 31 - __clz(int(m));
-      m &= ~(1u << r);
+    // (visiting only the rows with in-block dependants through a bit mask was measured slower than this
+    // fixed, unrolled loop: session J, profiles/r02)
+#pragma unroll 4
+    for (int step = 0; step < 32; ++step) {
+      const int r = DIR == 0 ? step : 31 - step;
+      if (r >= nr) continue; // warp-uniform
       double y[BS];
 #pragma unroll
       for (int d = 0; d < BS; ++d) y[d] = __shfl_sync(FULL, res[d], r);
@@ -497,6 +501,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   const int nb = int(blk_ptr.size()) - 1;
   std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), e_map, i_map, x_ptr(nb + 1, 0), x_ids;
   std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
+  std::vector<int> e_gcol;           // the same entries as factor rows (kernels without staging)
   std::vector<int> xloc(rowptr.size() - 1, -1); // factor row -> position in the current block's list
   int max_nx = 0;
   std::vector<unsigned> e_len(nb, 0u), i_mask(nb, 0u); // i_mask: local rows that occur as an intra-block column
@@ -540,14 +545,15 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
       lens |= unsigned(len) << (8 * q);
       const size_t base = e_col.size();
       e_col.resize(base + size_t(len) * 32, 0);
+      e_gcol.resize(base + size_t(len) * 32, 0);
       e_map.resize(base + size_t(len) * 32, -1);
       for (int l = 0; l < 32; ++l) {
         const std::vector<int> &ex = ext[srt[q * 8 + l / 4]];
         for (int k = 0; k < len; ++k) {
           const size_t o = base + size_t(k) * 32 + l;
           const size_t e = size_t(k) * 4 + (l & 3);
-          if (e < ex.size()) { e_col[o] = (unsigned short)xloc[colind[ex[e]]]; e_map[o] = ex[e]; }
-          else e_col[o] = 0; // padding: value 0 times the first staged row (len > 0 implies the list is not empty)
+          if (e < ex.size()) { e_col[o] = (unsigned short)xloc[colind[ex[e]]]; e_gcol[o] = colind[ex[e]]; e_map[o] = ex[e]; }
+          else { e_col[o] = 0; e_gcol[o] = x_ids[x_ptr[b]]; } // padding: value 0 times the block's first outside row
         }
       }
     }
@@ -591,7 +597,7 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   out.x_ids.upload(x_ids.empty() ? std::vector<int>(1, 0) : x_ids);
   out.n_ext = int64_t(e_col.size());
   out.n_int = int64_t(i_col.size());
-  out.e_ptr.upload(e_ptr); out.e_lix.upload(e_col); out.e_map.upload(e_map);
+  out.e_ptr.upload(e_ptr); out.e_lix.upload(e_col); out.e_col.upload(e_gcol); out.e_map.upload(e_map);
   out.e_len.upload(e_len); out.e_prow.upload(e_prow);
   out.e_val.alloc(e_col.size());
   out.i_ptr.upload(i_ptr); out.i_map.upload(i_map); out.i_off.upload(i_off); out.i_col.upload(i_col);
@@ -614,14 +620,14 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
   if (need > size_t(48) * 1024) {
     const int lim = int(need);
     if (ilu.bs_rhs == 3) {
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     } else if (ilu.bs_rhs == 2) {
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     } else {
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      NSB_CUDA(cudaFuncSetAttribute(k_bsell<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     }
   }
 }
@@ -643,10 +649,13 @@ template <int BS, int DIR>
 static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, int colour, int b0, int b1, double *yp,
                          const TrsvIo *io)
 {
-  const int max_nx = B.col_max_nx[colour];
+  // staging pays for the pressure matrix (long rows, one right-hand side: the sweeps are latency-bound) and
+  // costs occupancy for the 3-component velocity block (measured, profiles/r02 sessions H-J)
+  constexpr bool STAGE = BS == 1;
+  const int max_nx = STAGE ? B.col_max_nx[colour] : 0;
   const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
-  k_bsell<BS, DIR><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_val.p,
+  k_bsell<BS, DIR, STAGE><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_col.p, B.e_val.p,
                                                      B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp,
                                                      ilu.dinv.p, ilu.order.p, io, B.max_int, max_nx, int(wb));
 }

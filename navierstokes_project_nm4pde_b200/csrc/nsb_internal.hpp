@@ -115,6 +115,7 @@ struct DevBsell {
   int64_t n_ext = 0, n_int = 0;
   DevBuf<int> e_ptr, e_map;         // e_ptr[b]: first ext slot of block b (multiple of 32)
   DevBuf<unsigned short> e_lix;     // per ext slot: index into the block's list of distinct outside rows
+  DevBuf<int> e_col;                // per ext slot: the same as a factor row (sweeps that do not stage)
   DevBuf<int> x_ptr, x_ids;         // per block: its distinct outside rows (factor rows), staged into shared memory once
   DevBuf<unsigned> e_len;           // steps of the four ext passes of each block (one byte each)
   DevBuf<unsigned char> e_prow;     // [n_blocks][32] local row of each (pass, slot)
