@@ -64,7 +64,7 @@ WORKLOADS = {"cyl3d-20M": ("3d", (8, 40)), "cyl3d-16M": ("3d", (8, 32)), "cyl3d-
 DELTAT = {"3d": 2e-4, "2d": 0.01}          # main3D.cpp:38, main2D.cpp:22
 PRECOND = {"3d": "yosida", "2d": "asimple"}  # NavierStokes3D.cpp:562, NavierStokes2D.cpp:547
 N_DOFS = {"cyl3d-20M": 19923035, "cyl3d-2M": 2059237, "cyl3d-500k": 530456}
-AUTO_BLOCK_MIN_DOFS = 8e6                   # --ilu-ordering -1: block multicolour ILU above this many DoF per GPU
+AUTO_BLOCK_MIN_DOFS = 1.5e7                  # --ilu-ordering -1: block multicolour ILU above this many DoF per GPU
 PREP_INNER_RTOL = 1e-4                      # inner tolerance of the two untimed start-up steps
 PREP_STEPS = 2
 
@@ -465,7 +465,7 @@ def main():
                     help="mesh of the bounded CPU sample (cpu_baseline leg and --impl reference); default by core count")
     ap.add_argument("--ilu-ordering", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
                     help="0: natural row order (reference replay), 1: multicolour ILU(0), 2: block multicolour ILU(0), "
-                         "3: subdomain-resident ILU(0) (throughput modes); -1 (default): 2 above 8 M DoF per GPU, else 1 "
+                         "3: subdomain-resident ILU(0) (throughput modes); -1 (default): 2 above 15 M DoF per GPU, else 1 "
                          "(measured: the block sweeps need large colours, profiles/README.md)")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")

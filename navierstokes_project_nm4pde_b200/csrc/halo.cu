@@ -140,6 +140,7 @@ void halo_set_plan(Handle &H, int n_nb, const int *nb_rank, const int *send_node
                    const int *recv_node_cnt, const int *send_p_ptr, const int *send_p_idx, const int *recv_p_cnt)
 {
   Halo &h = *H.halo;
+  h.p2p = false; // a new plan: back to NCCL until nsb_p2p_export / nsb_p2p_attach are called again
   h.n_nb = n_nb;
   h.nb_rank.assign(nb_rank, nb_rank + n_nb);
   h.send_node_ptr.assign(send_node_ptr, send_node_ptr + n_nb + 1);
@@ -226,6 +227,16 @@ void halo_p2p_export(Handle &H, void *handle64)
   Halo &h = *H.halo;
   if (int(h.recv_node_ptr.size()) != h.n_nb + 1) throw StateError("nsb_p2p_export before nsb_set_halo");
   const long long nvals_u = (long long)(H.dim) * (H.n_nodes - H.n_nodes_owned), nvals_p = H.n_p - H.n_p_owned;
+  if (h.p2p || (h.mailbox && h.mailbox_bytes != mailbox_size(nvals_u, nvals_p))) {
+    // a new mesh / halo plan: drop the old mapping (peers hold stale offsets), start the sequences again
+    for (size_t r = 0; r < h.peer_base.size(); ++r)
+      if (h.peer_base[r] && int(r) != H.rank) cudaIpcCloseMemHandle(h.peer_base[r]);
+    h.peer_base.clear();
+    if (h.mailbox) cudaFree(h.mailbox);
+    h.mailbox = nullptr;
+    h.p2p = false;
+    h.seq_u = h.seq_p = h.seq_ar = 0;
+  }
   if (!h.mailbox) {
     h.mailbox_bytes = mailbox_size(nvals_u, nvals_p);
     NSB_CUDA(cudaMalloc(&h.mailbox, h.mailbox_bytes));

@@ -228,13 +228,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// spin until *f >= seq; a peer that never arrives traps the kernel (an error instead of a hang)
+// spin until *f >= seq.  Ranks run the same sequence of exchanges but their hosts may be skewed by seconds
+// (I/O between steps, a first-call graph capture): the limit is generous (~2 minutes); a peer that never
+// arrives still ends in a trap -- an error on this rank -- instead of a hung GPU.
 __device__ __forceinline__ void wait_flag(const unsigned long long *f, unsigned long long seq)
 {
   const long long t0 = clock64();
   while (ld_acquire_sys(f) < seq) {
     __nanosleep(40);
-    if (clock64() - t0 > 20000000000LL) __trap();
+    if (clock64() - t0 > 240000000000LL) __trap();
   }
 }
 // All-reduce (sum) of n <= kArSlots values held one per thread (thread j holds value j) of ONE block;

@@ -183,10 +183,10 @@ class DistributedNavierStokes(NavierStokes):
 
         import torch.distributed as dist
 
-        # Verified on 2 GPUs (parity tests + bench).  The one 8-GPU run of round 1 did not finish inside
-        # the GPU budget left, so above 2 ranks the default stays on NCCL until that is re-measured;
-        # NSB_P2P=1 / 0 forces either transport at any rank count.
-        want = os.environ.get("NSB_P2P", "1" if self.nranks <= 2 else "0")
+        # Verified on 2, 4 and 8 GPUs (parity tests at 2 and 4 ranks over both transports; the 19.9 M-DoF bench
+        # at 8 ranks: 30.8 ms per outer iteration against 33.2 ms over NCCL, profiles/README.md), so peer memory
+        # is the default at any rank count the mailbox supports; NSB_P2P=1 / 0 forces either transport.
+        want = os.environ.get("NSB_P2P", "1" if self.nranks <= 16 else "0")
         if want == "0" or dist.get_backend() != "nccl":
             return "nccl"
         try:

@@ -173,3 +173,64 @@ def test_midsize_parity_against_the_oracle():
     its_e, _, _ = e.solve_step()
     assert rc == 0 and abs(its_e - its_o) <= 2, (its_e, its_o)
     assert T.rel_l2(e.get_solution()[: d.n_u], o.array("sol_owned", d.N)[: d.n_u]) < 1e-5
+
+
+def test_2d_refined_cylinder_2M_properties():
+    """BASELINE.json configs[3]: the globally refined 2D cylinder (~2 M DoF, `bench.py` workload `cyl2d-2M`,
+    NavierStokes2D + aSIMPLE with inner GMRES on the Schur complement, NavierStokes2D.cpp:547,
+    Preconditioners.hpp:254-311) through the 2D kernels at bench size: divergence of a constant field,
+    linearity and block composition of the system SpMV, the rhs / F.1 identity of assemble_time_step
+    (with the Temam term, which 2D keeps), the ILU(0) applies, one reference time step whose true
+    preconditioned residual has dropped to the inner tolerance, and drag / lift on the device against
+    the host face loop on the downloaded solution."""
+    dt = bench.DELTAT["2d"]
+    (s,) = bench.WORKLOADS["cyl2d-2M"][1]
+    p = NavierStokes(HostMesh.cylinder2d(s), "2d", T=1.0, deltat=dt, test_case=2, ilu_ordering=1, orthogonalisation=1)
+    p.setup()
+    assert 1.5e6 < p.N < 3e6
+    e, nu, rng = p.engine, p.n_u, np.random.default_rng(20240607)
+    x0 = np.zeros(p.N)
+    x0[:nu] = 0.1 * rng.uniform(-1.0, 1.0, nu)
+    e.set_solution(x0)
+    e.set_dirichlet_values(p.dirichlet_values(2.0 + dt))
+    e.assemble_first(dt)
+    # B c = 0
+    y = e.block_vmult("B", np.tile([0.3, -1.1], nu // 2))
+    scale = np.abs(e.block_vmult("B", rng.uniform(-1.0, 1.0, nu))).max()
+    assert np.abs(y).max() < 1e-11 * scale
+    # linearity + blocks
+    x, z = rng.uniform(-1, 1, p.N), rng.uniform(-1, 1, p.N)
+    lhs = e.system_vmult(0.37 * x - 2.5 * z)
+    rhs = 0.37 * e.system_vmult(x) - 2.5 * e.system_vmult(z)
+    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
+    yy = e.system_vmult(x)
+    assert np.linalg.norm(yy[:nu] - e.block_vmult("F", x[:nu]) - e.block_vmult("Bt", x[nu:])) < 1e-13 * np.linalg.norm(yy[:nu])
+    # constant advecting state: rhs = c (F 1) on unconstrained rows (Temam term vanishes for div c = 0)
+    c = np.array([0.8, -0.4])
+    xc = np.zeros(p.N)
+    xc[:nu] = np.tile(c, nu // 2)
+    e.set_solution(xc)
+    e.assemble_step(2 * dt)
+    F1 = e.block_vmult("F", np.ones(nu))
+    m = np.ones(nu, bool)
+    m[p._dir_rows] = False
+    expect = np.tile(c, nu // 2) * F1
+    assert np.abs(e.get_rhs()[:nu][m] - expect[m]).max() < 1e-11 * np.abs(expect[m]).max()
+    # ILU(0) applies are linear
+    e.precond_init()
+    xu, zu = rng.uniform(-1, 1, nu), rng.uniform(-1, 1, nu)
+    lhs = e.ilu_apply(0, 0.5 * xu - 3.0 * zu)
+    rhs = 0.5 * e.ilu_apply(0, xu) - 3.0 * e.ilu_apply(0, zu)
+    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
+    # one time step from the rough state
+    e.set_solution(x0)
+    e.assemble_step(2 * dt)
+    its, _, _ = e.solve_step()
+    assert its > 0 and e.stat("n_F_solves") == e.stat("n_S_solves") > 0  # aSIMPLE: one F and one Schur solve per vmult
+    xs, b = e.get_solution(), e.get_rhs()
+    zr, z0 = e.precond_vmult(b - e.system_vmult(xs)), e.precond_vmult(b)
+    assert np.isfinite(zr).all() and np.linalg.norm(zr) < 5e-2 * np.linalg.norm(z0)
+    # drag / lift: device kernel == host face loop on the same field
+    f_dev = e.compute_forces()
+    f_host = p.dofs.boundary_forces(xs, 3, p.nu, 1.0)
+    assert np.allclose(f_dev, f_host, rtol=1e-10, atol=1e-13 * np.abs(f_host).max())
