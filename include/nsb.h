@@ -175,7 +175,11 @@ int nsb_compute_forces(nsb_handle h, double rho, double *out);
 /* replaces: VectorTools::interpolate(u_0) -> solution_owned; solution = solution_owned
  * (src/NavierStokes2D.cpp:708-709).  x has n_u + n_p entries [u block | p block] (local). */
 int nsb_set_solution(nsb_handle h, const double *x);
-int nsb_get_solution(nsb_handle h, double *x);
+int nsb_get_solution(nsb_handle h, double *x); /* multi-rank: ghost entries are refreshed first (collective) */
+/* replaces: Utilities::MPI::sum / MPI_Reduce of a few doubles (src/NavierStokes3D.cpp:830-831,
+ * Convergence3D.cpp:785-790): vals[n] (n <= 64) summed over all ranks in place, on the engine's transport
+ * (collective: every rank calls; a no-op on one rank) */
+int nsb_allreduce_sum(nsb_handle h, double *vals, int32_t n);
 
 /* ---- the hot path --------------------------------------------------------------------- */
 /* replaces: NavierStokes::assemble(time)            src/NavierStokes2D.cpp:164-357 */
@@ -295,6 +299,32 @@ int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, do
 int nsh_write_vtu(nsh_mesh m, nsh_dofs d, const double *solution, const char *path);
 /* Partition cells into nparts (recursive coordinate bisection); part[n_cells]. */
 int nsh_partition_cells(nsh_mesh m, int nparts, int32_t *part);
+
+/* replaces: GridTools::partition_triangulation + parallel::fullydistributed::Triangulation + the Epetra maps
+ * (src/NavierStokes2D.cpp:16-19, 71-87) for `rank` of `nranks`: the local (owned + two-layer ghost) cells in
+ * local numbering (owned DoFs first, ghosts grouped by owner rank and sorted by global id) and the ghost
+ * exchange plan of nsb_set_halo -- worked out from the replicated mesh without any communication.  The arrays
+ * are what nsb_set_mesh / nsb_set_halo take; *_gid map local -> global, g2l_* global -> local (-1: not local). */
+typedef struct nsh_local_s *nsh_local;
+nsh_local nsh_local_create(nsh_mesh m, nsh_dofs d, int32_t nranks, int32_t rank);
+void nsh_local_free(nsh_local l);
+int32_t nsh_local_n_cells(nsh_local l);
+int32_t nsh_local_n_nodes(nsh_local l);       /* local P2 nodes, owned + ghost */
+int32_t nsh_local_n_p(nsh_local l);
+int32_t nsh_local_n_nodes_owned(nsh_local l);
+int32_t nsh_local_n_p_owned(nsh_local l);
+const int32_t *nsh_local_cells(nsh_local l);      /* [n_cells] global cell ids, ascending */
+const int32_t *nsh_local_cell_part(nsh_local l);  /* [global cells] owner rank of every cell */
+const int32_t *nsh_local_cell_dofs(nsh_local l);  /* [n_cells][dofs_per_cell], local numbering */
+const double *nsh_local_cell_coords(nsh_local l); /* [n_cells][dim+1][dim] */
+const int32_t *nsh_local_node_gid(nsh_local l);
+const int32_t *nsh_local_p_gid(nsh_local l);
+const int32_t *nsh_local_g2l_node(nsh_local l);   /* [global nodes] */
+const int32_t *nsh_local_g2l_cell(nsh_local l);   /* [global cells] */
+/* the seven arrays of nsb_set_halo; returns the number of neighbours */
+int32_t nsh_local_halo(nsh_local l, const int32_t **nb_ranks, const int32_t **send_node_ptr, const int32_t **send_node_idx,
+                       const int32_t **recv_node_cnt, const int32_t **send_p_ptr, const int32_t **send_p_idx,
+                       const int32_t **recv_p_cnt);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

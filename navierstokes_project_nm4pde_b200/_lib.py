@@ -51,6 +51,7 @@ SIGNATURES = {
     "nsb_compute_forces": (C.c_int, [_H, C.c_double, c_double_p]),
     "nsb_set_solution": (C.c_int, [_H, c_double_p]),
     "nsb_get_solution": (C.c_int, [_H, c_double_p]),
+    "nsb_allreduce_sum": (C.c_int, [_H, c_double_p, C.c_int32]),
     "nsb_assemble_first": (C.c_int, [_H, C.c_double]),
     "nsb_assemble_step": (C.c_int, [_H, C.c_double]),
     "nsb_solve_step": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -104,6 +105,22 @@ SIGNATURES = {
     "nsh_boundary_forces": (C.c_int, [_H, _H, c_double_p, C.c_int32, C.c_double, C.c_double, c_double_p]),
     "nsh_write_vtu": (C.c_int, [_H, _H, c_double_p, C.c_char_p]),
     "nsh_partition_cells": (C.c_int, [_H, C.c_int, c_int_p]),
+    "nsh_local_create": (_H, [_H, _H, C.c_int32, C.c_int32]),
+    "nsh_local_free": (None, [_H]),
+    "nsh_local_n_cells": (C.c_int32, [_H]),
+    "nsh_local_n_nodes": (C.c_int32, [_H]),
+    "nsh_local_n_p": (C.c_int32, [_H]),
+    "nsh_local_n_nodes_owned": (C.c_int32, [_H]),
+    "nsh_local_n_p_owned": (C.c_int32, [_H]),
+    "nsh_local_cells": (c_int_p, [_H]),
+    "nsh_local_cell_part": (c_int_p, [_H]),
+    "nsh_local_cell_dofs": (c_int_p, [_H]),
+    "nsh_local_cell_coords": (c_double_p, [_H]),
+    "nsh_local_node_gid": (c_int_p, [_H]),
+    "nsh_local_p_gid": (c_int_p, [_H]),
+    "nsh_local_g2l_node": (c_int_p, [_H]),
+    "nsh_local_g2l_cell": (c_int_p, [_H]),
+    "nsh_local_halo": (C.c_int32, [_H] + [C.POINTER(c_int_p)] * 7),
 }
 
 _lib = None

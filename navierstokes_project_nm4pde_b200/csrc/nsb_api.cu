@@ -619,7 +619,23 @@ extern "C" int nsb_get_solution(nsb_handle h, double *x)
 {
   return guarded(h, [&](Handle &H) {
     if (!H.finalized) throw StateError("setup not finalized");
+    if (H.nranks > 1) { // solution = solution_owned: ghost import (NavierStokes2D.cpp:637)
+      halo_exchange_u(H, H.d_sol.p, H.ghost_off_u());
+      halo_exchange_p(H, H.d_sol.p + H.nu_owned(), H.ghost_off_p());
+    }
     download_vec(H, H.d_sol.p, x);
+  });
+}
+extern "C" int nsb_allreduce_sum(nsb_handle h, double *vals, int32_t n)
+{
+  return guarded(h, [&](Handle &H) {
+    if (!H.finalized) throw StateError("setup not finalized");
+    if (!vals || n < 1 || n > 64) throw ArgError("nsb_allreduce_sum: 1 <= n <= 64 values required");
+    if (H.nranks <= 1) return;
+    double *dev = H.ws->scal.p + 192; // device scalars not used by the solvers
+    h2d(H, dev, vals, sizeof(double) * size_t(n));
+    halo_allreduce(H, dev, n);
+    reduce_fetch(H, dev, n, vals);
   });
 }
 extern "C" int nsb_get_rhs(nsb_handle h, double *x)

@@ -7,6 +7,10 @@
 
 struct nsh_mesh_s { nsb::Mesh M; };
 struct nsh_dofs_s { nsb::Dofs D; };
+namespace nsb { // for host_local.cpp
+const Mesh &mesh_of(const nsh_mesh_s *m) { return m->M; }
+const Dofs &dofs_of(const nsh_dofs_s *d) { return d->D; }
+} // namespace nsb
 
 extern "C" {
 

@@ -100,3 +100,55 @@ def test_mailbox_protocol_emulation():
             if pc[r] == 2 * n_ex:
                 done += 1
     assert dim == 3
+
+
+@pytest.mark.parametrize("case_name,world", [("cyl3d", 8), ("cyl2d", 4), ("cube", 2)])
+def test_host_local_problem_matches_python_plan(case_name, world):
+    """nsh_local_* (csrc/host_local.cpp, what the C++ NavierStokes class uses under a launcher) derives the
+    local problem AND the exchange plan of every rank from the replicated mesh with no message; it must be
+    identical to the plan distributed.py negotiates with an all-to-all."""
+    import ctypes as C
+
+    from navierstokes_project_nm4pde_b200._lib import lib
+
+    L = lib()
+    case = T.Case(case_name)
+    d, dim = case.dofs, case.dim
+    part = case.mesh.partition(world)
+    locs = [D.build_local_problem(dim, d.cell_dofs(), d.cell_coords(), d.n_nodes, d.n_p, part, world, r) for r in range(world)]
+    sends = {(kind, r): [locs[r]["need_" + kind].get(q, np.zeros(0, np.int64)).astype(np.int64) for q in range(world)]
+             for kind in ("nodes", "p") for r in range(world)}
+    for r in range(world):
+        calls = iter(["nodes", "p"])
+        def a2a(_send, r=r, calls=calls):
+            kind = next(calls)
+            return [sends[(kind, q)][r] for q in range(world)]
+
+        want = D.halo_arrays(locs[r], *D.exchange_requests(locs[r], world, r, a2a))
+        h = C.c_void_p(L.nsh_local_create(case.mesh.h, d.h, world, r))
+        assert h
+        try:
+            arr = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.int32)  # noqa: E731
+            nc, nn, npl = L.nsh_local_n_cells(h), L.nsh_local_n_nodes(h), L.nsh_local_n_p(h)
+            loc = locs[r]
+            assert np.array_equal(arr(L.nsh_local_cell_part(h), d.n_cells), part)
+            assert np.array_equal(arr(L.nsh_local_cells(h), nc), loc["cells"])
+            assert L.nsh_local_n_nodes_owned(h) == loc["n_nodes_owned"] and L.nsh_local_n_p_owned(h) == loc["n_p_owned"]
+            assert np.array_equal(arr(L.nsh_local_node_gid(h), nn), loc["node_gid"])
+            assert np.array_equal(arr(L.nsh_local_p_gid(h), npl), loc["p_gid"])
+            assert np.array_equal(arr(L.nsh_local_cell_dofs(h), nc * d.dpc).reshape(nc, -1), loc["cell_dofs"])
+            cc = np.ctypeslib.as_array(L.nsh_local_cell_coords(h), shape=(nc, dim + 1, dim))
+            assert np.array_equal(cc, loc["cell_coords"])
+            assert np.array_equal(arr(L.nsh_local_g2l_node(h), d.n_nodes), loc["g2l_node"])
+            g2c = arr(L.nsh_local_g2l_cell(h), d.n_cells)
+            assert np.array_equal(np.nonzero(g2c >= 0)[0], loc["cells"])
+            ptrs = [C.POINTER(C.c_int32)() for _ in range(7)]
+            nnb = L.nsh_local_halo(h, *[C.byref(p) for p in ptrs])
+            assert nnb == want[0].size
+            got_nb = arr(ptrs[0], nnb)
+            snp, spp = arr(ptrs[1], nnb + 1), arr(ptrs[4], nnb + 1)
+            got = (got_nb, snp, arr(ptrs[2], int(snp[-1])), arr(ptrs[3], nnb), spp, arr(ptrs[5], int(spp[-1])), arr(ptrs[6], nnb))
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+        finally:
+            L.nsh_local_free(h)
