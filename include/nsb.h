@@ -294,6 +294,9 @@ int nsh_boundary_forces(nsh_mesh m, nsh_dofs d, const double *solution, int32_t 
 /* replaces: VectorTools::point_value (src/NavierStokes2D.cpp:875-889): velocity components and
  * pressure of the solution vector [u | p] at point x, out[dim + 1]; NSB_ERR_ARG when no cell holds x */
 int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out);
+/* the cell VectorTools::point_value evaluates in: first cell holding x (barycentric coordinates lam[dim + 1]
+ * filled), -1 when none does; lets a rank of a multi-rank run evaluate only the points of the cells it owns */
+int32_t nsh_dofs_find_cell(nsh_dofs d, const double *x, double *lam);
 /* minimal stand-in for DataOut::write_vtu (src/NavierStokes2D.cpp:642-675): ASCII .vtu, linear cells,
  * point data "velocity" and "pressure" of the solution vector [u | p] */
 int nsh_write_vtu(nsh_mesh m, nsh_dofs d, const double *solution, const char *path);

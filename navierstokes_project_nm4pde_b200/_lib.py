@@ -103,6 +103,7 @@ SIGNATURES = {
     "nsh_dofs_boundary_faces": (C.c_int32, [_H, _H, C.c_int32, c_int_p, c_int_p]),
     "nsh_dofs_point_value": (C.c_int, [_H, c_double_p, c_double_p, c_double_p]),
     "nsh_boundary_forces": (C.c_int, [_H, _H, c_double_p, C.c_int32, C.c_double, C.c_double, c_double_p]),
+    "nsh_dofs_find_cell": (C.c_int32, [_H, c_double_p, c_double_p]),
     "nsh_write_vtu": (C.c_int, [_H, _H, c_double_p, C.c_char_p]),
     "nsh_partition_cells": (C.c_int, [_H, C.c_int, c_int_p]),
     "nsh_local_create": (_H, [_H, _H, C.c_int32, C.c_int32]),

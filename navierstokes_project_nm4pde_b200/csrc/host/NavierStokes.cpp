@@ -90,6 +90,7 @@ NavierStokes::NavierStokes(Variant variant_, const std::string &mesh_file_name_,
 NavierStokes::~NavierStokes()
 {
   if (engine) nsb_destroy(engine);
+  if (local) nsh_local_free(local);
   if (dofs) nsh_dofs_free(dofs);
   if (mesh) nsh_mesh_free(mesh);
 }
@@ -100,6 +101,20 @@ void NavierStokes::check(int rc, const char *what) const
   const char *msg = nsb_last_error(engine);
   throw std::runtime_error(std::string(what) + ": " + (msg ? msg : "error") + " (code " + std::to_string(rc) + ")");
 }
+
+void NavierStokes::set_parallel(int nranks_, int rank_, AllGather allgather_)
+{
+  if (engine) throw std::logic_error("NavierStokes::set_parallel must precede setup()");
+  if (nranks_ < 1 || rank_ < 0 || rank_ >= nranks_) throw std::invalid_argument("NavierStokes::set_parallel: bad rank");
+  if (nranks_ > 1 && !allgather_) throw std::invalid_argument("NavierStokes::set_parallel: an all-gather is required");
+  nranks = nranks_;
+  rank = rank_;
+  allgather = std::move(allgather_);
+  verbose = verbose && rank == 0; // pcout (NavierStokes2D.hpp:103)
+}
+
+const double *NavierStokes::node_xyz(int i) const { return nsh_dofs_node_xyz(dofs) + size_t(dim) * (node_gid ? node_gid[i] : i); }
+const double *NavierStokes::p_xyz(int i) const { return nsh_dofs_p_xyz(dofs) + size_t(dim) * (p_gid ? p_gid[i] : i); }
 
 // NavierStokes::setup (NavierStokes2D.cpp:2-157)
 void NavierStokes::setup()
@@ -119,57 +134,141 @@ void NavierStokes::setup()
   if (nsh_mesh_dim(mesh) != dim) throw std::runtime_error("mesh dimension does not match the problem class");
   if (verbose) std::cout << "  Number of elements = " << nsh_mesh_n_cells(mesh) << std::endl;
   dofs = nsh_dofs_create(mesh);
-  n_nodes = nsh_dofs_n_nodes(dofs);
-  n_u = dim * n_nodes;
-  n_p = nsh_dofs_n_p(dofs);
-  N = n_u + n_p;
+  if (!dofs) throw std::runtime_error("DoF numbering failed");
+  const int n_nodes_global = nsh_dofs_n_nodes(dofs), n_p_global = nsh_dofs_n_p(dofs);
+  N_global = dim * n_nodes_global + n_p_global;
   dpc = nsh_dofs_per_cell(dofs);
-  if (verbose) std::cout << "  Number of DoFs = " << N << " (" << n_u << " + " << n_p << ")" << std::endl;
+  if (verbose)
+    std::cout << "  Number of DoFs = " << N_global << " (" << dim * n_nodes_global << " + " << n_p_global << ")" << std::endl;
 
-  // Dirichlet nodes (interpolate_boundary_values, NavierStokes2D.cpp:328-353; Convergence3D.cpp:364-368)
+  // Partition (NavierStokes2D.cpp:16-19) and the locally relevant DoFs (:71-87); on one rank local == global.
+  int n_nodes_owned, n_p_owned;
+  const int32_t *g2l_node = nullptr;
+  if (nranks > 1) {
+    local = nsh_local_create(mesh, dofs, nranks, rank);
+    if (!local) throw std::runtime_error("partitioning failed");
+    n_cells = nsh_local_n_cells(local);
+    n_nodes = nsh_local_n_nodes(local);
+    n_p = nsh_local_n_p(local);
+    n_nodes_owned = nsh_local_n_nodes_owned(local);
+    n_p_owned = nsh_local_n_p_owned(local);
+    cell_dofs = nsh_local_cell_dofs(local);
+    cell_coords = nsh_local_cell_coords(local);
+    node_gid = nsh_local_node_gid(local);
+    p_gid = nsh_local_p_gid(local);
+    cell_gid = nsh_local_cells(local);
+    cell_owner = nsh_local_cell_part(local);
+    g2l_cell = nsh_local_g2l_cell(local);
+    g2l_node = nsh_local_g2l_node(local);
+  } else {
+    n_cells = nsh_mesh_n_cells(mesh);
+    n_nodes = n_nodes_owned = n_nodes_global;
+    n_p = n_p_owned = n_p_global;
+    cell_dofs = nsh_dofs_cell_dofs(dofs);
+    cell_coords = nsh_dofs_cell_coords(dofs);
+  }
+  n_u = dim * n_nodes;
+  N = n_u + n_p;
+
+  // Dirichlet nodes (interpolate_boundary_values, NavierStokes2D.cpp:328-353; Convergence3D.cpp:364-368); ghost
+  // nodes included: their rows of B^T are cleared too
   auto boundary_nodes = [&](std::initializer_list<int32_t> ids) {
     std::vector<int32_t> idv(ids), out(size_t(nsh_dofs_boundary_nodes(dofs, mesh, idv.data(), int32_t(idv.size()), nullptr)));
     nsh_dofs_boundary_nodes(dofs, mesh, idv.data(), int32_t(idv.size()), out.data());
     return out;
   };
+  std::vector<int32_t> dir_global;
+  std::vector<char> inlet_global;
   if (variant == Variant::Convergence3D) {
-    dir_nodes = boundary_nodes({0, 1, 2, 4, 5});
-    dir_is_inlet.assign(dir_nodes.size(), 0);
+    dir_global = boundary_nodes({0, 1, 2, 4, 5});
+    inlet_global.assign(dir_global.size(), 0);
   } else {
     const std::vector<int32_t> inlet = boundary_nodes({0}), walls = boundary_nodes({2, 3});
-    std::vector<char> on_inlet(size_t(n_nodes), 0), on_wall(size_t(n_nodes), 0);
+    std::vector<char> on_inlet(size_t(n_nodes_global), 0), on_wall(size_t(n_nodes_global), 0);
     for (int32_t v : inlet) on_inlet[v] = 1;
     for (int32_t v : walls) on_wall[v] = 1;
-    dir_nodes = inlet;
+    dir_global = inlet;
     for (int32_t v : walls)
-      if (!on_inlet[v]) dir_nodes.push_back(v);
-    for (int32_t v : dir_nodes) dir_is_inlet.push_back(on_inlet[v] && !on_wall[v]); // the second call overwrites with zero
+      if (!on_inlet[v]) dir_global.push_back(v);
+    for (int32_t v : dir_global) inlet_global.push_back(on_inlet[v] && !on_wall[v]); // the second call overwrites with zero
+  }
+  for (size_t k = 0; k < dir_global.size(); ++k) {
+    const int32_t v = g2l_node ? g2l_node[dir_global[k]] : dir_global[k];
+    if (v < 0) continue;
+    dir_nodes.push_back(v);
+    dir_is_inlet.push_back(inlet_global[k]);
   }
   for (int32_t v : dir_nodes)
     for (int c = 0; c < dim; ++c) dir_rows.push_back(dim * v + c);
-  const int32_t nf = nsh_dofs_boundary_faces(dofs, mesh, 3, nullptr, nullptr);
-  obstacle_cells.resize(size_t(nf));
-  obstacle_faces.resize(size_t(nf));
-  if (nf) nsh_dofs_boundary_faces(dofs, mesh, 3, obstacle_cells.data(), obstacle_faces.data());
+  // faces with boundary id 3 (the obstacle; the Neumann face of the cube): those in local cells, flagged when
+  // this rank owns the cell (cell->is_locally_owned(), NavierStokes2D.cpp:781)
+  {
+    const int32_t nf = nsh_dofs_boundary_faces(dofs, mesh, 3, nullptr, nullptr);
+    std::vector<int32_t> fc(static_cast<size_t>(nf)), fl(static_cast<size_t>(nf));
+    if (nf) nsh_dofs_boundary_faces(dofs, mesh, 3, fc.data(), fl.data());
+    for (int32_t f = 0; f < nf; ++f) {
+      const int32_t k = g2l_cell ? g2l_cell[fc[f]] : fc[f];
+      if (k < 0) continue;
+      obstacle_cells.push_back(k);
+      obstacle_faces.push_back(fl[f]);
+      obstacle_owned.push_back(!cell_owner || cell_owner[fc[f]] == rank);
+    }
+  }
 
-  int rc = nsb_create(&engine, dim, device, 1, 0, nullptr);
+  unsigned char nccl_id[128] = {0};
+  if (nranks > 1) { // ncclGetUniqueId on rank 0, broadcast through the all-gather
+    if (rank == 0 && nsb_get_unique_id(nccl_id) < 0) throw std::runtime_error(std::string("nsb_get_unique_id: ") + nsb_last_error(nullptr));
+    std::vector<unsigned char> all(size_t(128) * nranks);
+    allgather(nccl_id, all.data(), 128);
+    std::copy(all.begin(), all.begin() + 128, nccl_id);
+  }
+  int rc = nsb_create(&engine, dim, device, nranks, rank, nranks > 1 ? nccl_id : nullptr);
   if (rc < 0) throw std::runtime_error(std::string("nsb_create: ") + nsb_last_error(nullptr));
   nsb_params prm;
   check(nsb_default_params(&prm, int(variant)), "nsb_default_params");
   prm.nu = nu;
   prm.deltat = deltat;
   prm.ilu_ordering = ilu_ordering;
+  prm.orthogonalisation = orthogonalisation;
   check(nsb_set_params(engine, &prm), "nsb_set_params");
-  check(nsb_set_mesh(engine, nsh_mesh_n_cells(mesh), nsh_dofs_cell_coords(dofs), nsh_dofs_cell_dofs(dofs), n_u, n_p, n_u,
-                     n_p),
-        "nsb_set_mesh");
+  check(nsb_set_mesh(engine, n_cells, cell_coords, cell_dofs, n_u, n_p, dim * n_nodes_owned, n_p_owned), "nsb_set_mesh");
   const Rule q = gauss_simplex(dim); // QGaussSimplex<dim>(fe->degree + 1), NavierStokes2D.cpp:45
   check(nsb_set_quadrature(engine, q.size(), q.xi.data(), q.w.data()), "nsb_set_quadrature");
+  if (nranks > 1) {
+    const int32_t *nb, *snp, *sni, *rnc, *spp, *spi, *rpc;
+    const int32_t nnb = nsh_local_halo(local, &nb, &snp, &sni, &rnc, &spp, &spi, &rpc);
+    check(nsb_set_halo(engine, nnb, nb, snp, sni, rnc, spp, spi, rpc), "nsb_set_halo");
+  }
   check(nsb_finalize_setup(engine), "nsb_finalize_setup");
+  if (nranks > 1) { // peer-memory transport: every rank maps every rank's mailbox; all ranks or none (NSB_P2P=0: NCCL)
+    transport_name = "nccl";
+    const char *want = std::getenv("NSB_P2P");
+    if (!(want && want[0] == '0') && nranks <= 16) {
+      unsigned char mine[65] = {0}; // 64-byte handle + "export worked"
+      mine[64] = nsb_p2p_export(engine, mine) >= 0;
+      std::vector<unsigned char> all(size_t(65) * nranks), handles(size_t(64) * nranks);
+      allgather(mine, all.data(), 65);
+      bool ok = true;
+      for (int r = 0; r < nranks; ++r) {
+        ok = ok && all[size_t(65) * r + 64];
+        std::copy(all.begin() + 65 * r, all.begin() + 65 * r + 64, handles.begin() + 64 * r);
+      }
+      unsigned char attached = ok && nsb_p2p_attach(engine, handles.data()) >= 0;
+      std::vector<unsigned char> flags(size_t(nranks), 0);
+      allgather(&attached, flags.data(), 1);
+      const bool all_attached = std::all_of(flags.begin(), flags.end(), [](unsigned char f) { return f != 0; });
+      if (attached && !all_attached) throw std::runtime_error("peer-memory transport came up on some ranks only");
+      if (all_attached) transport_name = "p2p";
+    }
+    if (verbose) std::cout << "  " << nranks << " ranks, transport " << transport_name << std::endl;
+  }
   check(nsb_set_dirichlet(engine, int32_t(dir_rows.size()), dir_rows.data()), "nsb_set_dirichlet");
-  if (variant != Variant::Convergence3D) { // compute_forces runs on the device: obstacle faces + face rule
+  if (variant != Variant::Convergence3D) { // compute_forces runs on the device: obstacle faces of owned cells + face rule
+    std::vector<int32_t> fc, fl;
+    for (size_t f = 0; f < obstacle_cells.size(); ++f)
+      if (obstacle_owned[f]) { fc.push_back(obstacle_cells[f]); fl.push_back(obstacle_faces[f]); }
     const Rule qf = gauss_simplex(dim - 1); // QGauss<1>(3) (NavierStokes2D.cpp:758) / QGaussSimplex<2>(3)
-    check(nsb_set_force_faces(engine, nf, obstacle_cells.data(), obstacle_faces.data(), qf.size(), qf.xi.data(), qf.w.data()),
+    check(nsb_set_force_faces(engine, int32_t(fc.size()), fc.data(), fl.data(), qf.size(), qf.xi.data(), qf.w.data()),
           "nsb_set_force_faces");
   }
   solution.assign(size_t(N), 0.0);
@@ -177,10 +276,9 @@ void NavierStokes::setup()
 
 void NavierStokes::dirichlet_values(double time, std::vector<double> &vals) const
 {
-  const double *xyz = nsh_dofs_node_xyz(dofs);
   vals.assign(dir_rows.size(), 0.0);
   for (size_t k = 0; k < dir_nodes.size(); ++k) {
-    const double *x = xyz + size_t(dim) * dir_nodes[k];
+    const double *x = node_xyz(dir_nodes[k]);
     if (variant == Variant::Convergence3D) {
       double u[3], p, g[3][3];
       ethier_steinman(x, time, u, p, g);
@@ -196,8 +294,8 @@ void NavierStokes::neumann_rhs(double time, std::vector<double> &rhs) const
 {
   rhs.assign(size_t(n_u), 0.0);
   const Rule q = gauss_simplex(2);
-  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
-  const double *cc = nsh_dofs_cell_coords(dofs);
+  const int32_t *cd = cell_dofs; // every face touching an owned node lies in a local cell (two-layer halo)
+  const double *cc = cell_coords;
   for (size_t f = 0; f < obstacle_cells.size(); ++f) {
     const int c = obstacle_cells[f], lf = obstacle_faces[f];
     int vs[3], nv = 0;
@@ -241,14 +339,13 @@ void NavierStokes::initial_condition(std::vector<double> &x) const
 {
   x.assign(size_t(N), 0.0); // FunctionU0 = 0 for the cylinders (NavierStokes2D.hpp:140-150)
   if (variant != Variant::Convergence3D) return;
-  const double *nx = nsh_dofs_node_xyz(dofs), *px = nsh_dofs_p_xyz(dofs);
   double u[3], p, g[3][3];
   for (int n = 0; n < n_nodes; ++n) {
-    ethier_steinman(nx + size_t(3) * n, 0.0, u, p, g);
+    ethier_steinman(node_xyz(n), 0.0, u, p, g);
     for (int c = 0; c < 3; ++c) x[size_t(3) * n + c] = u[c];
   }
   for (int v = 0; v < n_p; ++v) {
-    ethier_steinman(px + size_t(3) * v, 0.0, u, p, g);
+    ethier_steinman(p_xyz(v), 0.0, u, p, g);
     x[size_t(n_u) + v] = p;
   }
 }
@@ -283,7 +380,7 @@ void NavierStokes::solve_time_step(double)
     std::cout << "Time taken to solve Navier Stokes problem: " << ts << " seconds" << std::endl;
     std::cout << "Result:  " << its << " GMRES iterations" << std::endl;
   }
-  if (write_output && variant == Variant::Cylinder2D) { // gmres.csv: time, Re, iterations (NavierStokes2D.cpp:622-636)
+  if (write_output && rank == 0 && variant == Variant::Cylinder2D) { // gmres.csv: time, Re, iterations (NavierStokes2D.cpp:622-636)
     const int Re = int(0.1 * 1.5 * std::sin(time_now * kPi / 8.0) / .001);
     std::ofstream gm("gmres.csv", std::ios::app);
     if (gm.is_open()) gm << time_now << ',' << Re << ',' << its << "\n";
@@ -324,10 +421,13 @@ void NavierStokes::output(unsigned time_step, const std::vector<double> &coeff) 
   char num[16];
   std::snprintf(num, sizeof(num), "%03u", time_step);
   const std::string path = dir + name + "_" + num + ".vtu";
-  sync_solution();
-  if (nsh_write_vtu(mesh, dofs, solution.data(), path.c_str()) != 0) throw std::runtime_error("cannot write " + path);
-  if (verbose) std::cout << "Output written to " << name << std::endl;
-  if (variant == Variant::Cylinder2D && coeff.size() >= 2) {
+  if (nranks == 1) {
+    sync_solution();
+    if (nsh_write_vtu(mesh, dofs, solution.data(), path.c_str()) != 0) throw std::runtime_error("cannot write " + path);
+    if (verbose) std::cout << "Output written to " << name << std::endl;
+  } else if (verbose && time_step == 0)
+    std::cout << "(.vtu pieces are not written in multi-rank runs: output is outside the device path)" << std::endl;
+  if (rank == 0 && variant == Variant::Cylinder2D && coeff.size() >= 2) {
     std::ofstream coeff_file("coeff_2.csv", std::ios::app); // append mode as the reference (:682)
     if (coeff_file.is_open()) coeff_file << time_step << "," << coeff[0] << "," << coeff[1] << "\n";
   }
@@ -339,11 +439,37 @@ void NavierStokes::compute_pressure_difference()
 {
   const double pa[3] = {0.45, 0.2, 0.205}, pe[3] = {0.55, 0.2, 0.205};
   double va[4], ve[4];
-  sync_solution();
-  const double p1 = nsh_dofs_point_value(dofs, solution.data(), pa, va) == 0 ? va[dim] : 0.0;
-  const double p2 = nsh_dofs_point_value(dofs, solution.data(), pe, ve) == 0 ? ve[dim] : 0.0;
+  const double p1 = point_value(pa, va) ? va[dim] : 0.0;
+  const double p2 = point_value(pe, ve) ? ve[dim] : 0.0;
   pressure_difference = p1 - p2;
   if (verbose) std::cout << "Pressure difference (P(A) - P(B)) = " << pressure_difference << std::endl;
+}
+
+// VectorTools::point_value on the distributed solution: the rank that owns the cell holding x evaluates it from
+// its local vector, the others contribute zero, and the values are summed over the ranks (collective).
+bool NavierStokes::point_value(const double *x, double *out) const
+{
+  sync_solution();
+  if (nranks == 1) return nsh_dofs_point_value(dofs, solution.data(), x, out) == 0;
+  double lam[4], acc[5] = {0, 0, 0, 0, 0}; // dim + 1 values and "found"
+  const int32_t c = nsh_dofs_find_cell(dofs, x, lam);
+  if (c >= 0 && cell_owner[c] == rank) {
+    const int32_t *cd = cell_dofs + size_t(g2l_cell[c]) * dpc;
+    const int nv1 = dim + 1, n2 = dim == 2 ? 6 : 10;
+    for (int v = 0; v < nv1; ++v) {
+      const double ph = lam[v] * (2.0 * lam[v] - 1.0);
+      for (int k = 0; k < dim; ++k) acc[k] += ph * solution[cd[v * nv1 + k]];
+      acc[dim] += lam[v] * solution[cd[v * nv1 + dim]];
+    }
+    for (int e = 0; e < n2 - nv1; ++e) {
+      const double ph = 4.0 * lam[kEdges[e][0]] * lam[kEdges[e][1]];
+      for (int k = 0; k < dim; ++k) acc[k] += ph * solution[cd[nv1 * nv1 + e * dim + k]];
+    }
+    acc[4] = 1.0;
+  }
+  check(nsb_allreduce_sum(engine, acc, 5), "nsb_allreduce_sum");
+  for (int k = 0; k <= dim; ++k) out[k] = acc[k];
+  return acc[4] > 0.5;
 }
 
 // NavierStokes::solve (NavierStokes2D.cpp:699-750, NavierStokes3D.cpp:694-742, Convergence3D.cpp:724-764)
@@ -393,11 +519,11 @@ double NavierStokes::compute_error(const VectorTools::NormType &norm_type)
 {
   sync_solution();
   const Rule q = gauss_simplex(3);
-  const int32_t *cd = nsh_dofs_cell_dofs(dofs);
-  const double *cc = nsh_dofs_cell_coords(dofs);
-  const int nc = nsh_mesh_n_cells(mesh);
+  const int32_t *cd = cell_dofs;
+  const double *cc = cell_coords;
   double e2 = 0.0, h2 = 0.0;
-  for (int c = 0; c < nc; ++c) {
+  for (int c = 0; c < n_cells; ++c) {
+    if (cell_owner && cell_owner[cell_gid[c]] != rank) continue; // locally owned cells, then the sum over ranks
     const double *X = cc + size_t(c) * 12;
     double gl[4][3];
     const double det = bary_gradients(3, X, gl);
@@ -428,5 +554,7 @@ double NavierStokes::compute_error(const VectorTools::NormType &norm_type)
       }
     }
   }
-  return norm_type == VectorTools::L2_norm ? std::sqrt(e2) : std::sqrt(e2 + h2);
+  double sums[2] = {e2, h2}; // Utilities::MPI::sum of the squared cell errors (Convergence3D.cpp:785-790)
+  check(nsb_allreduce_sum(engine, sums, 2), "nsb_allreduce_sum");
+  return norm_type == VectorTools::L2_norm ? std::sqrt(sums[0]) : std::sqrt(sums[0] + sums[1]);
 }

@@ -10,6 +10,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,16 @@ public:
   NavierStokes(const NavierStokes &) = delete;
   NavierStokes &operator=(const NavierStokes &) = delete;
 
+  // One process per GPU -- the reference under `mpirun -n P` (main3D.cpp:9,28; the partition of
+  // NavierStokes2D.cpp:16-19).  Call before setup(); `allgather(mine, all, bytes)` is MPI_Allgather of small
+  // blobs (host/rendezvous.hpp in the drivers) and is used during setup() only: per-step traffic is
+  // device-to-device inside the library.  Only rank 0 prints (pcout).
+  using AllGather = std::function<void(const void *mine, void *all, size_t bytes)>;
+  void set_parallel(int nranks, int rank, AllGather allgather);
+  int this_mpi_process() const { return rank; }
+  int n_mpi_processes() const { return nranks; }
+  const char *transport() const { return transport_name; } // "single", "nccl" or "p2p" (peer memory over NVLink)
+
   void setup();
   void solve();
   double compute_error(const VectorTools::NormType &norm_type); // Convergence3D.cpp:766-794
@@ -43,14 +54,16 @@ public:
 
   // knobs the reference hard-codes; the drivers override them from the environment
   int max_steps = -1;        // stop after this many steps (reference: run to T)
-  int ilu_ordering = 0;      // 0: reference replay, 1: multicolour throughput mode
+  int ilu_ordering = 0;      // 0: reference replay, 1 / 2 / 3: throughput orderings (nsb_params)
+  int orthogonalisation = 0; // 0: modified Gram-Schmidt as SolverGMRES, 1: batched (throughput mode)
   int device = 0;
   double forces_after = 0.1; // NavierStokes3D.cpp:728 computes forces only for time > 0.1
   bool write_output = false; // VTU per step (2D) / every 20 steps (3D), gmres.csv, coeff_2.csv as the reference
   bool verbose = true;
 
+  // local vector [u (owned, ghost) | p (owned, ghost)]; the whole vector on one rank
   const std::vector<double> &get_solution() { sync_solution(); return solution; }
-  int n_dofs() const { return N; }
+  int n_dofs() const { return N_global; }
 
 protected:
   void assemble(const double &time);           // NavierStokes2D.cpp:164-357
@@ -64,6 +77,9 @@ protected:
   void initial_condition(std::vector<double> &x) const;          // NavierStokes2D.cpp:708
   void check(int rc, const char *what) const;
   void sync_solution() const; // device -> host copy of the solution, only when a host consumer needs it
+  bool point_value(const double *x, double *out) const; // VectorTools::point_value + sum over the ranks
+  const double *node_xyz(int local_node) const;
+  const double *p_xyz(int local_p) const;
 
   Variant variant;
   int dim;
@@ -75,11 +91,22 @@ protected:
 
   nsh_mesh mesh = nullptr;
   nsh_dofs dofs = nullptr;
+  nsh_local local = nullptr; // subdomain of this rank (nranks > 1)
   nsb_handle engine = nullptr;
-  int n_nodes = 0, n_u = 0, n_p = 0, N = 0, dpc = 0;
+  int nranks = 1, rank = 0;
+  AllGather allgather;
+  const char *transport_name = "single";
+  // sizes and index arrays below are LOCAL to this rank (owned + ghost); on one rank local == global
+  int n_nodes = 0, n_u = 0, n_p = 0, N = 0, N_global = 0, dpc = 0, n_cells = 0;
+  const int32_t *cell_dofs = nullptr;  // [n_cells][dpc]
+  const double *cell_coords = nullptr; // [n_cells][dim+1][dim]
+  const int32_t *node_gid = nullptr, *p_gid = nullptr; // local -> global (null: identity)
+  const int32_t *cell_gid = nullptr, *cell_owner = nullptr, *g2l_cell = nullptr;
   std::vector<int32_t> dir_nodes, dir_rows;
   std::vector<char> dir_is_inlet;
-  std::vector<int32_t> obstacle_cells, obstacle_faces; // boundary id 3: owning cell, local face
+  // boundary id 3 faces lying in local cells: local cell, local face, and whether this rank owns the cell
+  std::vector<int32_t> obstacle_cells, obstacle_faces;
+  std::vector<char> obstacle_owned;
   mutable std::vector<double> solution; // host mirror of the device solution (see sync_solution)
   mutable bool solution_stale = false;
   double time_now = 0.0;

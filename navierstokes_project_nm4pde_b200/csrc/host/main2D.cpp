@@ -12,12 +12,16 @@ int main(int argc, char *argv[])
   dealii::Timer timer;
   timer.restart();
   try {
+    Utilities::MPI::MPI_InitFinalize mpi_init(argc, argv);                                 // main2D.cpp:9
+    const unsigned int mpi_rank = Utilities::MPI::this_mpi_process(mpi_init);
+    if (rendezvous_selftest(mpi_init)) return 0;
     NavierStokes problem(NavierStokes::Variant::Cylinder2D, mesh_file_name, degree_velocity, degree_pressure, T, deltat,
                          test_case);
-    apply_env(problem);
+    apply_env(problem, mpi_init);
     problem.setup();
     problem.solve();
     timer.stop();
+    if (mpi_rank != 0) return 0;
     std::cout << "Time taken to solve ENTIRE Navier Stokes problem: " << timer.wall_time() << " seconds" << std::endl;
     return write_forces_csv("forces_results_2D_2case.csv", problem, deltat);
   } catch (const std::exception &e) {

@@ -21,26 +21,34 @@ int main(int argc, char *argv[])
 
   dealii::Timer timer;
   timer.restart();
-  std::ofstream convergence_file("convergence.csv");
-  convergence_file << "h,eL2,eH1" << std::endl;
   std::vector<double> errors_L2, errors_H1;
+  unsigned int mpi_rank = 0;
   try {
+    Utilities::MPI::MPI_InitFinalize mpi_init(argc, argv);                        // main_convergence3D.cpp:13
+    mpi_rank = Utilities::MPI::this_mpi_process(mpi_init);
+    if (rendezvous_selftest(mpi_init)) return 0;
+    std::ofstream convergence_file;
+    if (mpi_rank == 0) {
+      convergence_file.open("convergence.csv");
+      convergence_file << "h,eL2,eH1" << std::endl;
+    }
     for (unsigned int i = 0; i < meshes.size(); ++i) {
       NavierStokes problem(NavierStokes::Variant::Convergence3D, meshes[i], degree_velocity, degree_pressure, T, deltat);
-      apply_env(problem);
+      apply_env(problem, mpi_init);
       problem.setup();
       problem.solve();
       const double error_L2 = problem.compute_error(VectorTools::L2_norm);
       const double error_H1 = problem.compute_error(VectorTools::H1_norm);
       errors_L2.push_back(error_L2);
       errors_H1.push_back(error_H1);
-      convergence_file << h_vals[i] << "," << error_L2 << "," << error_H1 << std::endl;
+      if (mpi_rank == 0) convergence_file << h_vals[i] << "," << error_L2 << "," << error_H1 << std::endl;
       timer.stop();
     }
   } catch (const std::exception &e) {
     std::cerr << "convergence: " << e.what() << std::endl;
     return 1;
   }
+  if (mpi_rank != 0) return 0;
   std::cout << "Time taken to solve ENTIRE Navier Stokes problem: " << timer.wall_time() << " seconds" << std::endl;
   // ConvergenceTable::evaluate_all_convergence_rates(reduction_rate_log2)
   std::cout << "h        L2          rate   H1          rate" << std::endl;

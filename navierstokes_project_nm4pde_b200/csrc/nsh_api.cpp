@@ -126,20 +126,17 @@ int32_t nsh_dofs_boundary_faces(nsh_dofs d, nsh_mesh m, int32_t id, int32_t *fac
   return n;
 }
 
-// VectorTools::point_value of the (P2^dim, P1) solution at x: finds the cell containing x (first cell
-// whose barycentric coordinates are all >= -1e-10) and evaluates the dim velocity components and the
-// pressure there.  out[dim + 1]; returns 0, or NSB_ERR_ARG when no cell contains the point
-// (deal.II: ExcPointNotAvailableHere).
-int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out)
+// Cell containing x: the first cell whose barycentric coordinates are all >= -1e-10 (lam[dim + 1] filled),
+// or -1 when no cell holds the point (deal.II: ExcPointNotAvailableHere).
+int32_t nsh_dofs_find_cell(nsh_dofs d, const double *x, double *lam)
 {
-  if (!d || !solution || !x || !out) return NSB_ERR_ARG;
+  if (!d || !x || !lam) return -1;
   const nsb::Dofs &D = d->D;
-  const int dim = D.dim, nv1 = D.nv1, n2 = D.n2;
-  const int64_t n_u = int64_t(dim) * D.n_nodes;
+  const int dim = D.dim, nv1 = D.nv1;
   for (int64_t c = 0; c < D.nc; ++c) {
     const double *X = &D.cell_coords[size_t(c) * nv1 * dim];
     // solve J lam' = x - x0 for the barycentric coordinates lam_1..lam_dim
-    double J[3][3], b[3], lam[4];
+    double J[3][3], b[3];
     for (int r = 0; r < dim; ++r) {
       b[r] = x[r] - X[r];
       for (int k = 0; k < dim; ++k) J[r][k] = X[(k + 1) * dim + r] - X[r];
@@ -165,22 +162,36 @@ int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, do
     }
     bool inside = true;
     for (int v = 0; v < nv1; ++v) inside &= (lam[v] >= -1e-10);
-    if (!inside) continue;
-    for (int k = 0; k <= dim; ++k) out[k] = 0.0;
-    const int *cn = &D.cell_nodes[size_t(c) * n2];
-    const int *cp = &D.cell_p[size_t(c) * nv1];
-    for (int v = 0; v < nv1; ++v) {
-      const double ph = lam[v] * (2.0 * lam[v] - 1.0);
-      for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[v] + k];
-      out[dim] += lam[v] * solution[n_u + cp[v]];
-    }
-    for (int e = 0; e < n2 - nv1; ++e) {
-      const double ph = 4.0 * lam[nsb::kEdgeA[e]] * lam[nsb::kEdgeB[e]];
-      for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[nv1 + e] + k];
-    }
-    return NSB_OK;
+    if (inside) return int32_t(c);
   }
-  return NSB_ERR_ARG;
+  return -1;
+}
+
+// VectorTools::point_value of the (P2^dim, P1) solution at x: evaluates the dim velocity components and the
+// pressure in the cell nsh_dofs_find_cell returns.  out[dim + 1]; returns 0, or NSB_ERR_ARG when no cell
+// contains the point.
+int nsh_dofs_point_value(nsh_dofs d, const double *solution, const double *x, double *out)
+{
+  if (!d || !solution || !x || !out) return NSB_ERR_ARG;
+  const nsb::Dofs &D = d->D;
+  const int dim = D.dim, nv1 = D.nv1, n2 = D.n2;
+  const int64_t n_u = int64_t(dim) * D.n_nodes;
+  double lam[4];
+  const int32_t c = nsh_dofs_find_cell(d, x, lam);
+  if (c < 0) return NSB_ERR_ARG;
+  for (int k = 0; k <= dim; ++k) out[k] = 0.0;
+  const int *cn = &D.cell_nodes[size_t(c) * n2];
+  const int *cp = &D.cell_p[size_t(c) * nv1];
+  for (int v = 0; v < nv1; ++v) {
+    const double ph = lam[v] * (2.0 * lam[v] - 1.0);
+    for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[v] + k];
+    out[dim] += lam[v] * solution[n_u + cp[v]];
+  }
+  for (int e = 0; e < n2 - nv1; ++e) {
+    const double ph = 4.0 * lam[nsb::kEdgeA[e]] * lam[nsb::kEdgeB[e]];
+    for (int k = 0; k < dim; ++k) out[k] += ph * solution[size_t(dim) * cn[nv1 + e] + k];
+  }
+  return NSB_OK;
 }
 
 // Minimal stand-in for DataOut::write_vtu (src/NavierStokes2D.cpp:642-675): one ASCII .vtu with the

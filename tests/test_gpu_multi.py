@@ -179,3 +179,108 @@ def test_ranks_match_block_jacobi_oracle(case_name, ordering, orth, transport, w
             assert abs(res[0][1][step] - its_o) <= 1 and its_o > 100, (step, res[0][1], its_o)
             assert T.rel_l2(xe[: case.n_u], xo[: case.n_u]) < 1e-4, step
             break
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The C++ NavierStokes class and its drivers, one process per GPU (the reference under mpirun, main3D.cpp:9,28)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "navierstokes_project_nm4pde_b200", "csrc", "host", "bin")
+LAUNCH = os.path.join(ROOT, "scripts", "nsb_launch.sh")
+
+
+def _solve_worker(rank, world, port, out_q):
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from navierstokes_project_nm4pde_b200 import Engine, HostMesh
+        from navierstokes_project_nm4pde_b200.distributed import DistributedNavierStokes
+
+        uid = [Engine.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        prob = DistributedNavierStokes(HostMesh.cylinder3d(1, 3), "3d", T=4.0, deltat=0.0002, test_case=2, device=rank,
+                                       nranks=world, rank=rank, unique_id=uid[0])
+        prob.forces_after = 0.0
+        prob.setup()
+        prob.solve(max_steps=3)
+        out_q.put((rank, prob.gmres_iterations, list(zip(prob.vec_drag_coeff, prob.vec_lift_coeff)), prob.transport))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_cpp_driver_two_ranks_matches_python_two_ranks(tmp_path, transport):
+    """navier_stokes3D started once per GPU by scripts/nsb_launch.sh (rendezvous.hpp: NCCL id and IPC handles over
+    TCP, subdomains from nsh_local_*) against the Python multi-rank class on the same mesh: same partition, same
+    engine calls, hence the same outer iteration counts and force coefficients."""
+    import re
+    import subprocess
+
+    from navierstokes_project_nm4pde_b200 import Engine
+
+    if Engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, NSB_MAX_STEPS="3", NSB_FORCES_AFTER="0", NSB_P2P="1" if transport == "p2p" else "0",
+               NSB_RDV_PORT=str(_free_port()))
+    r = subprocess.run([LAUNCH, "2", os.path.join(BIN, "navier_stokes3D"), "gen:cylinder3d:1:3"], capture_output=True, text=True,
+                       env=env, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert f"2 ranks, transport {transport}" in out
+    its_cpp = [int(m) for m in re.findall(r"Result:\s+(\d+) GMRES iterations", out)]
+    coeff_cpp = [(float(a), float(b)) for a, b in re.findall(r"Coeff:\s+(\S+) Coeff:\s+(\S+)", out)]
+    assert len(its_cpp) == 3 and len(coeff_cpp) == 3
+    assert "Result" not in (tmp_path / "rank1.log").read_text()  # only rank 0 prints (pcout)
+
+    import torch.multiprocessing as mp
+
+    os.environ["NSB_P2P"] = "1" if transport == "p2p" else "0"
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_solve_worker, args=(k, 2, port, q)) for k in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=240) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        os.environ.pop("NSB_P2P", None)
+    assert res[0][3] == transport
+    assert its_cpp == res[0][1] == res[1][1]
+    assert np.allclose(np.array(coeff_cpp), np.array(res[0][2]), rtol=1e-5, atol=1e-9)  # 6 printed digits
+
+
+def test_cpp_convergence_driver_two_ranks(tmp_path):
+    """Ethier-Steinman driver on 2 ranks (Neumann face term, exact Dirichlet data and initial state through the
+    local numbering; compute_error summed over the ranks): the errors equal the single-rank run to solver
+    tolerance and the orders hold."""
+    import math
+    import subprocess
+
+    from navierstokes_project_nm4pde_b200 import Engine
+
+    if Engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    errs = {}
+    for n in (1, 2):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        r = subprocess.run([LAUNCH, str(n), os.path.join(BIN, "convergence"), "gen:cube:4", "gen:cube:8"], capture_output=True,
+                           text=True, env=dict(os.environ, NSB_RDV_PORT=str(_free_port())), cwd=d, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rows = (d / "convergence.csv").read_text().strip().splitlines()[1:]
+        errs[n] = np.array([[float(v) for v in ln.split(",")] for ln in rows])
+    assert errs[2].shape == (2, 3)
+    assert np.allclose(errs[1], errs[2], rtol=2e-2)
+    assert 2.5 < math.log2(errs[2][0, 1] / errs[2][1, 1]) < 3.6 and 1.6 < math.log2(errs[2][0, 2] / errs[2][1, 2]) < 2.6

@@ -278,3 +278,21 @@ def test_subdomain_ilu_storage_cpu(gen, dim, bs, leaf):
         assert err.value < 1e-12, err.value
         assert stats[0] >= 2 and 0 < stats[1] <= n and stats[3] <= 65535
         assert stats[6] == (1 if levels[1] == 0 else 3) or stats[1] == n
+
+
+def test_driver_rendezvous_without_gpu(tmp_path):
+    """The launcher contract of the C++ drivers (csrc/host/rendezvous.hpp, scripts/nsb_launch.sh): three
+    processes find each other over TCP and all-gather blobs of 1 B .. 100 kB; no GPU is touched."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "navierstokes_project_nm4pde_b200", "csrc", "host", "bin", "navier_stokes3D")
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} is not built (make -C navierstokes_project_nm4pde_b200/csrc drivers)")
+    r = subprocess.run([os.path.join(root, "scripts", "nsb_launch.sh"), "3", exe], capture_output=True, text=True,
+                       env=dict(os.environ, NSB_RDV_SELFTEST="1"), cwd=tmp_path, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rendezvous ok: rank 0 of 3" in r.stdout
+    for k in (1, 2):
+        assert f"rendezvous ok: rank {k} of 3" in (tmp_path / f"rank{k}.log").read_text()
