@@ -1343,6 +1343,72 @@ static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
   }
 }
 
+// NSB_PDL (default off): chain the colour sweeps of a triangular solve by programmatic dependent launch
+// (nsb_internal.hpp).  Read when a solve is captured.
+bool pdl_enabled()
+{
+  const char *e = getenv("NSB_PDL");
+  return e ? atoi(e) != 0 : false; // off until measured on hardware
+}
+
+// NSB_L2_PERSIST_MB (default 0 = off): set aside that much of the L2 for persisting lines and mark the staging
+// vector of the captured solve as persisting (hit ratio = set-aside / window): a colour sweep gathers rows that
+// OTHER colours wrote from the whole vector, which is larger than the L2 at 19.9 M DoF, so without a policy
+// every gather is a DRAM miss; with it a fixed subset of the vector stays resident across the sweeps.  The window is
+// attached to every kernel node of the captured graph (stream attributes are not inherited by captured nodes).
+static void ilu_graph_l2_policy(cudaGraph_t g, void *base, size_t bytes)
+{
+  const char *e = getenv("NSB_L2_PERSIST_MB");
+  const size_t want = e ? size_t(std::max(0, atoi(e))) << 20 : 0;
+  if (!want || !bytes) return;
+  int dev = 0;
+  cudaDeviceProp prop;
+  NSB_CUDA(cudaGetDevice(&dev));
+  NSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  const size_t set_aside = std::min<size_t>(want, size_t(prop.persistingL2CacheMaxSize));
+  if (!set_aside || prop.accessPolicyMaxWindowSize <= 0) return;
+  NSB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+  cudaKernelNodeAttrValue v = {};
+  v.accessPolicyWindow.base_ptr = base;
+  v.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, size_t(prop.accessPolicyMaxWindowSize));
+  v.accessPolicyWindow.hitRatio = float(std::min(1.0, double(set_aside) / double(v.accessPolicyWindow.num_bytes)));
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  size_t n = 0;
+  NSB_CUDA(cudaGraphGetNodes(g, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  NSB_CUDA(cudaGraphGetNodes(g, nodes.data(), &n));
+  for (cudaGraphNode_t node : nodes) {
+    cudaGraphNodeType t;
+    NSB_CUDA(cudaGraphNodeGetType(node, &t));
+    if (t == cudaGraphNodeTypeKernel) NSB_CUDA(cudaGraphKernelNodeSetAttribute(node, cudaKernelNodeAttributeAccessPolicyWindow, &v));
+  }
+  if (getenv("NSB_VERBOSE"))
+    fprintf(stderr, "[nsb] L2 policy: %zu MB set aside (max %d MB), window %zu MB (max %d MB), hit ratio %.2f, %zu nodes\n",
+            set_aside >> 20, prop.persistingL2CacheMaxSize >> 20, v.accessPolicyWindow.num_bytes >> 20,
+            prop.accessPolicyMaxWindowSize >> 20, v.accessPolicyWindow.hitRatio, n);
+}
+
+// drop the captured solves (they are re-captured, with the current NSB_PDL / NSB_L2_* settings, on the next use)
+void ilu_reset_graphs(Handle &H)
+{
+  for (DevIlu *ilu : {&H.iluF, &H.iluS}) {
+    if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
+    if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
+  }
+  // device-wide L2 knobs follow the environment of the next capture (profiling: scripts/prof_variants.py)
+  static size_t fetch_default = 0;
+  if (!fetch_default && cudaDeviceGetLimit(&fetch_default, cudaLimitMaxL2FetchGranularity) != cudaSuccess) fetch_default = 0;
+  const char *e = getenv("NSB_L2_FETCH"); // hint: DRAM -> L2 fetch granularity in bytes (32 / 64 / 128)
+  const size_t gbytes = e && atoi(e) > 0 ? size_t(atoi(e)) : fetch_default;
+  if (gbytes) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gbytes);
+  if (!getenv("NSB_L2_PERSIST_MB")) {
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  }
+  cudaGetLastError(); // the knobs are hints: a refusal is not an error
+}
+
 // y = U^{-1} D^{-1} L^{-1} x.  The per-level launches are captured once into a CUDA graph that
 // works in place on a fixed staging vector (graph nodes bake their pointers).
 void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
@@ -1368,6 +1434,7 @@ void ilu_solve(Handle &H, DevIlu &ilu, const double *x, double *y)
     else if (ilu.bs_rhs == 2) trsv_levels<2>(H, ilu, ilu.graph_x, s);
     else trsv_levels<3>(H, ilu, ilu.graph_x, s);
     NSB_CUDA(cudaStreamEndCapture(s, &g));
+    ilu_graph_l2_policy(g, ilu.graph_x, sizeof(double) * stage);
     NSB_CUDA(cudaGraphInstantiate(&ilu.graph_f, g, 0));
     NSB_CUDA(cudaGraphDestroy(g));
     H.launches = before;

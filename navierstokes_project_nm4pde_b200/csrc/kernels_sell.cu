@@ -28,7 +28,8 @@ constexpr int kSM = 148;
 __device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c)
 {
   // the fourth double of the padded node is loaded into a scratch PTX register and dropped
-  asm("{ .reg .f64 pad; ld.global.v4.f64 {%0,%1,%2,pad}, [%3]; }" : "=d"(a), "=d"(b), "=d"(c) : "l"(p));
+  // (volatile: must not be scheduled above a preceding pdl_wait())
+  asm volatile("{ .reg .f64 pad; ld.global.v4.f64 {%0,%1,%2,pad}, [%3]; }" : "=d"(a), "=d"(b), "=d"(c) : "l"(p));
 }
 
 // in / out vectors of a captured triangular solve: the graph bakes kernel arguments, so the
@@ -58,13 +59,15 @@ __global__ void __launch_bounds__(256, U == 4 ? (MODE == 0 ? 6 : 5) : 3) k_sell3
   // stride would hand the same warps the long slices of every window (ncu: 52% achieved occupancy)
   const int lane = threadIdx.x & 31;
   const int s = s0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (MODE != 0) pdl_launch_dependents(); // the next colour's sweep may be scheduled (it blocks in pdl_wait)
   if (s < s1) {
     const int base = slice_ptr[s];
     const int len = (slice_ptr[s + 1] - base) >> 5;
     const int r = rowid[(int64_t(s) << 5) + lane];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     // row-local operands of the triangular sweeps are requested before the entry loop so that their
-    // latency (order -> x) overlaps it
+    // latency (order -> x) overlaps it.  Everything up to pdl_wait() is independent of the previous sweep
+    // (the caller's x is not written inside the chain) and overlaps its tail.
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, di = 1.0;
     int ro = 0;
     if (MODE != 0 && r >= 0) {
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(256, U == 4 ? (MODE == 0 ? 6 : 5) : 3) k_sell3
       c[u] = ok ? __ldcs(cp + u * 32) : 0;
       v[u] = ok ? __ldcs(vp + u * 32) : 0.0;
     }
+    if (MODE != 0) pdl_wait(); // the staging vector y is read (gathers, own row) only from here on
     for (int k = 0; k < len; k += U) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -230,17 +234,17 @@ int sell_lanes_for(int n_rows)
 
 template <int MODE, bool PAD>
 static void launch_sell(cudaStream_t s, const DevSell &S, int a, int b, int depth, const double *xp, double *y,
-                        const double *dinv, const int *order, const TrsvIo *io)
+                        const double *dinv, const int *order, const TrsvIo *io, bool pdl = false)
 {
   const unsigned g = sell_grid(b - a);
   const int *sp = S.slice_ptr.p, *ri = S.rowid.p, *cl = S.col.p;
   const double *vl = S.val.p;
   if (S.lanes == 4) {
-    if (depth == 8) k_sell3<MODE, 8, PAD, 4><<<g, 256, 0, s>>>(a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
-    else k_sell3<MODE, 4, PAD, 4><<<g, 256, 0, s>>>(a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
+    if (depth == 8) launch_k(k_sell3<MODE, 8, PAD, 4>, g, 256, 0, s, pdl, a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
+    else launch_k(k_sell3<MODE, 4, PAD, 4>, g, 256, 0, s, pdl, a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
   } else {
-    if (depth == 8) k_sell3<MODE, 8, PAD, 1><<<g, 256, 0, s>>>(a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
-    else k_sell3<MODE, 4, PAD, 1><<<g, 256, 0, s>>>(a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
+    if (depth == 8) launch_k(k_sell3<MODE, 8, PAD, 1>, g, 256, 0, s, pdl, a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
+    else launch_k(k_sell3<MODE, 4, PAD, 1>, g, 256, 0, s, pdl, a, b, sp, ri, cl, vl, xp, y, dinv, order, io);
   }
 }
 
@@ -280,16 +284,20 @@ void sell_trsv(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
   const TrsvIo *io = reinterpret_cast<const TrsvIo *>(ilu.io.p);
   static const int depth_env = env_int("NSB_SELL_U", 0);
   const int depth = depth_env ? depth_env : (ilu.sellL.lanes == 4 ? 4 : 8);
+  const bool pdl = pdl_enabled();
+  bool chained = false; // the first sweep of the chain is an ordinary launch
   for (int c = 0; c < nc; ++c) {
     const int a = ilu.sellL.range_slice[c], b = ilu.sellL.range_slice[c + 1];
     if (b <= a) continue;
-    launch_sell<1, true>(s, ilu.sellL, a, b, depth, yp, yp, nullptr, ilu.order.p, io);
+    launch_sell<1, true>(s, ilu.sellL, a, b, depth, yp, yp, nullptr, ilu.order.p, io, pdl && chained);
+    chained = true;
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int a = ilu.sellU.range_slice[c], b = ilu.sellU.range_slice[c + 1];
     if (b <= a) continue;
-    launch_sell<2, true>(s, ilu.sellU, a, b, depth, yp, yp, ilu.dinv.p, ilu.order.p, io);
+    launch_sell<2, true>(s, ilu.sellU, a, b, depth, yp, yp, ilu.dinv.p, ilu.order.p, io, pdl && chained);
+    chained = true;
     H.launches++;
   }
   NSB_CUDA(cudaGetLastError());
@@ -337,11 +345,11 @@ __device__ __forceinline__ void bsell_gather(const double *yp, int c, double (&x
   if constexpr (BS == 3) ld256(yp + 4 * int64_t(c), x[0], x[1], x[2]);
   else if constexpr (BS == 2) {
     double a, b;
-    asm("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(yp + 2 * int64_t(c)));
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(yp + 2 * int64_t(c)));
     x[0] = a; x[1] = b;
   } else {
     double a;
-    asm("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(yp + c));
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(yp + c));
     x[0] = a;
   }
 }
@@ -368,6 +376,7 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   extern __shared__ __align__(16) unsigned char bsell_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = b0 + blockIdx.x * kBW + warp;
+  pdl_launch_dependents(); // the next colour's sweep may be scheduled (it blocks in pdl_wait)
   if (b >= b1) return; // the whole warp leaves; there is no block-wide barrier below
   unsigned char *base = bsell_smem + size_t(warp) * warp_bytes;
   double *acc = reinterpret_cast<double *>(base);
@@ -381,30 +390,18 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   double res[BS];
 #pragma unroll
   for (int d = 0; d < BS; ++d) res[d] = 0.0;
+  // ---- everything that does not depend on the previous sweep: row ids, the caller's x (not written inside the
+  // chain), the inverse diagonal, the in-block entries (into shared memory) -- overlaps the previous sweep's tail
   int ro = 0;
+  double di = 1.0;
   if (valid) {
     ro = order[row];
     if (DIR == 0) {
       const double *xi = io->x + int64_t(BS) * ro;
 #pragma unroll
       for (int d = 0; d < BS; ++d) res[d] = xi[d];
-    } else {
-      const double di = dinv[row];
-      const double *yi = yp + int64_t(PS) * row;
-#pragma unroll
-      for (int d = 0; d < BS; ++d) res[d] = yi[d] * di;
-    }
-  }
-  // ---- stage the distinct rows of other blocks this block couples with (each is used ~3 times): ONE
-  // round trip to HBM / L2 for all of them instead of one per step of the passes below
-  if (STAGE) {
-    const int xb = x_ptr[b], nx = min(x_ptr[b + 1] - xb, max_nx);
-    for (int k = lane; k < nx; k += 32) {
-      double x[BS];
-      bsell_gather<BS>(yp, x_ids[xb + k], x);
-#pragma unroll
-      for (int d = 0; d < BS; ++d) xs[k * BS + d] = x[d];
-    }
+    } else
+      di = dinv[row];
   }
   const int ib = i_ptr[b], ni = i_ptr[b + 1] - ib;
   for (int k = lane; k < ni; k += 32) {
@@ -412,13 +409,31 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
     scol[k] = i_col[ib + k];
   }
   for (int k = lane; k < 33; k += 32) soff[k] = i_off[size_t(b) * 33 + k];
+  const unsigned lens = e_len[b];
+  const int eb = e_ptr[b];
+  const int xb = STAGE ? x_ptr[b] : 0, nx = STAGE ? min(x_ptr[b + 1] - xb, max_nx) : 0;
+  pdl_wait(); // the staging vector yp is read only from here on
+  if (DIR == 1 && valid) {
+    const double *yi = yp + int64_t(PS) * row;
+#pragma unroll
+    for (int d = 0; d < BS; ++d) res[d] = yi[d] * di;
+  }
+  // ---- stage the distinct rows of other blocks this block couples with (each is used ~3 times): ONE
+  // round trip to HBM / L2 for all of them instead of one per step of the passes below
+  if (STAGE) {
+    for (int k = lane; k < nx; k += 32) {
+      double x[BS];
+      bsell_gather<BS>(yp, x_ids[xb + k], x);
+#pragma unroll
+      for (int d = 0; d < BS; ++d) xs[k * BS + d] = x[d];
+    }
+  }
   __syncwarp();
   // ---- entries coupling with other blocks: four passes of eight rows, four lanes per row
   {
-    const unsigned lens = e_len[b];
-    const unsigned short *cp = e_lix + e_ptr[b] + lane;
-    const int *gp = e_col + e_ptr[b] + lane;
-    const double *vp = e_val + e_ptr[b] + lane;
+    const unsigned short *cp = e_lix + eb + lane;
+    const int *gp = e_col + eb + lane;
+    const double *vp = e_val + eb + lane;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int len = int((lens >> (8 * q)) & 255u);
@@ -647,7 +662,7 @@ void bsell_fill(Handle &H, DevIlu &ilu)
 
 template <int BS, int DIR>
 static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, int colour, int b0, int b1, double *yp,
-                         const TrsvIo *io)
+                         const TrsvIo *io, bool pdl)
 {
   // staging pays for the pressure matrix (long rows, one right-hand side: the sweeps are latency-bound) and
   // costs occupancy for the 3-component velocity block (measured, profiles/r02 sessions H-J)
@@ -655,9 +670,9 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
   const int max_nx = STAGE ? B.col_max_nx[colour] : 0;
   const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
-  k_bsell<BS, DIR, STAGE><<<grid, kBW * 32, wb * kBW, s>>>(b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_col.p, B.e_val.p,
-                                                     B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp,
-                                                     ilu.dinv.p, ilu.order.p, io, B.max_int, max_nx, int(wb));
+  launch_k(k_bsell<BS, DIR, STAGE>, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p,
+           B.e_col.p, B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p,
+           ilu.order.p, io, B.max_int, max_nx, int(wb));
 }
 
 template <int BS>
@@ -665,16 +680,20 @@ static void bsell_trsv_t(Handle &H, DevIlu &ilu, double *yp, cudaStream_t s)
 {
   const int nc = int(ilu.colour_blk.size()) - 1;
   const TrsvIo *io = reinterpret_cast<const TrsvIo *>(ilu.io.p);
+  const bool pdl = pdl_enabled();
+  bool chained = false; // the first sweep of the chain is an ordinary launch
   for (int c = 0; c < nc; ++c) {
     const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
     if (b <= a) continue;
-    launch_bsell<BS, 0>(s, ilu, ilu.bL, c, a, b, yp, io);
+    launch_bsell<BS, 0>(s, ilu, ilu.bL, c, a, b, yp, io, pdl && chained);
+    chained = true;
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int a = ilu.colour_blk[c], b = ilu.colour_blk[c + 1];
     if (b <= a) continue;
-    launch_bsell<BS, 1>(s, ilu, ilu.bU, c, a, b, yp, io);
+    launch_bsell<BS, 1>(s, ilu, ilu.bU, c, a, b, yp, io, pdl && chained);
+    chained = true;
     H.launches++;
   }
 }

@@ -38,10 +38,35 @@ __global__ void __launch_bounds__(256) k_stream(const int *__restrict__ blk, con
                                                 const double *__restrict__ dinv)
 {
   __shared__ double prod[kCH * BS];
+  if (MODE != 0) pdl_launch_dependents(); // the next colour's sweep may be scheduled (it blocks in pdl_wait)
   const int r0 = blk[blockIdx.x], r1 = blk[blockIdx.x + 1];
   const int k0 = rowptr[r0], k1 = rowptr[r1];
   const int n = (k1 - k0) * BS;
   int t = threadIdx.x;
+  if constexpr (MODE != 0) {
+    // triangular sweep: the first four (entry, component) pairs of every thread -- the whole block for one
+    // right-hand side -- are loaded before pdl_wait(): they do not depend on the previous sweep and overlap its tail
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tt = t + u * 256;
+      const bool ok = tt < n;
+      const int e = tt / BS;
+      c[u] = ok ? __ldcs(colind + k0 + e) : 0;
+      v[u] = ok ? __ldcs(val + k0 + e) : 0.0;
+    }
+    pdl_wait(); // x (= y, the solution being swept) is read only from here on
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tt = t + u * 256;
+      if (tt < n) {
+        const int d = tt - (tt / BS) * BS;
+        prod[tt] = v[u] * x[int64_t(BS) * c[u] + (c[u] >= n_owned ? goff : 0) + d];
+      }
+    }
+    t += 4 * 256;
+  } else {
   for (; t + 3 * 256 < n; t += 4 * 256) {
     int c[4];
     double v[4], xv[4];
@@ -58,6 +83,7 @@ __global__ void __launch_bounds__(256) k_stream(const int *__restrict__ blk, con
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) prod[t + u * 256] = v[u] * xv[u];
+  }
   }
   for (; t < n; t += 256) {
     const int e = t / BS, d = t - e * BS;
@@ -280,16 +306,22 @@ template <int BS>
 static void stream_trsv_t(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
 {
   const int nc = int(ilu.colour_ptr.size()) - 1;
+  const bool pdl = pdl_enabled();
+  bool chained = false; // the first sweep of the chain is an ordinary launch
+  const double *yc = y;
+  const double *none = nullptr;
   for (int c = 1; c < nc; ++c) { // colour 0 has no lower part
     const int nb = ilu.cblkL[c + 1] - ilu.cblkL[c] - 1;
     if (nb <= 0) continue;
-    k_stream<BS, 1><<<nb, 256, 0, s>>>(ilu.blkL.p + ilu.cblkL[c], ilu.Lp.p, ilu.Lc.p, ilu.Lv.p, y, ilu.n, 0, y, nullptr);
+    launch_k(k_stream<BS, 1>, nb, 256, 0, s, pdl && chained, ilu.blkL.p + ilu.cblkL[c], ilu.Lp.p, ilu.Lc.p, ilu.Lv.p, yc, ilu.n, 0, y, none);
+    chained = true;
     H.launches++;
   }
   for (int c = nc - 1; c >= 0; --c) {
     const int nb = ilu.cblkU[c + 1] - ilu.cblkU[c] - 1;
     if (nb <= 0) continue;
-    k_stream<BS, 2><<<nb, 256, 0, s>>>(ilu.blkU.p + ilu.cblkU[c], ilu.Up.p, ilu.Uc.p, ilu.Uv.p, y, ilu.n, 0, y, ilu.dinv.p);
+    launch_k(k_stream<BS, 2>, nb, 256, 0, s, pdl && chained, ilu.blkU.p + ilu.cblkU[c], ilu.Up.p, ilu.Uc.p, ilu.Uv.p, yc, ilu.n, 0, y, ilu.dinv.p);
+    chained = true;
     H.launches++;
   }
 }

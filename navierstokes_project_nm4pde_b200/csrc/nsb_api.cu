@@ -335,10 +335,7 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     H.d_neumann.alloc(size_t(H.nu_owned()));
     H.d_neumann.zero();
     // ILU(0) schedules (static pattern => symbolic work once)
-    for (DevIlu *ilu : {&H.iluF, &H.iluS}) { // schedules are rebuilt: drop graphs captured for the old ones
-      if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
-      if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
-    }
+    ilu_reset_graphs(H); // schedules are rebuilt: drop graphs captured for the old ones
     phase("mesh arrays, vectors");
     stream_build_spmv(H);
     if (dim == 3) {
@@ -949,6 +946,13 @@ extern "C" int nsb_bench_kernel(nsb_handle h, const char *which, int iters, int 
     const double nu = double(H.nu_owned()), np = double(H.n_p_owned);
     double bytes = 0;
     std::function<void()> run;
+    if (w == "reset_graphs") { // profiling hook: re-capture the triangular solves under the current environment
+      sync(H);
+      ilu_reset_graphs(H);
+      if (ms_per_launch) *ms_per_launch = 0;
+      if (bytes_per_launch) *bytes_per_launch = 0;
+      return;
+    }
     if (w == "spmv_system") {
       // values + column index of every stored entry, row pointers, x read once, y written once
       bytes = 12.0 * H.Fs.nnz + (8.0 * dim + 4.0) * (H.Bt.nnz + H.B.nnz) + 4.0 * (2.0 * H.n_nodes_owned + np) +

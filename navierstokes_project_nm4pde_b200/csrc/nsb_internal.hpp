@@ -27,6 +27,37 @@ struct NcclError : std::runtime_error { using std::runtime_error::runtime_error;
                            std::to_string(__LINE__) + ")");                                        \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+) for chains of dependent sweeps (one launch per colour of a
+// triangular solve).  A sweep kernel calls pdl_launch_dependents() first -- the next sweep of the chain may then be
+// scheduled while this one runs -- reads everything that does NOT depend on the previous sweep (row ids, matrix
+// entries, diagonal), and calls pdl_wait() before its first access to the solution vector: the wait returns when the
+// preceding grid has completed and its writes are visible.  Without the launch attribute both are no-ops, so the
+// same kernels serve ordinary launches.  launch_k() launches with the attribute when `pdl` is set; it is captured
+// into CUDA graphs as a programmatic edge.  NSB_PDL=0 switches it off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  NSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+#endif
+bool pdl_enabled(); // kernels_linalg.cu: NSB_PDL (read when a solve is captured)
+struct Handle;
+void ilu_reset_graphs(Handle &H);
+
 constexpr int kMaxQ = 16;
 
 // reference-element tables, uploaded once (nsb_set_quadrature)
