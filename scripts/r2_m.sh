@@ -9,12 +9,10 @@ tail -4 gpurun_out/r2m_pytest_pdl.log
 timeout 200 python -m pytest tests/test_gpu_parity.py -q -k "multicolour or batched" > gpurun_out/r2m_pytest_nopdl.log 2>&1; echo "pytest(nopdl) rc=$?" >> gpurun_out/r2m_pytest_nopdl.log
 tail -3 gpurun_out/r2m_pytest_nopdl.log
 V2="NSB_PDL=0;NSB_L2_FETCH=32;NSB_L2_FETCH=128;NSB_PDL=1;NSB_PDL=1,NSB_L2_FETCH=32"
-for o in 1 2; do
-  timeout 150 python scripts/prof_variants.py cyl3d-2M $o 10 "$V2" 2>&1 | tee gpurun_out/r2m_prof_2M_o$o.log
-done
+timeout 150 python scripts/prof_variants.py cyl3d-2M 1 10 "$V2" 2>&1 | tee gpurun_out/r2m_prof_2M_o1.log
+timeout 150 python scripts/prof_variants.py cyl3d-2M 2 10 "$V2;NSB_BSELL_OCC=10;NSB_PDL=1,NSB_BSELL_OCC=10" 2>&1 | tee gpurun_out/r2m_prof_2M_o2.log
 V20="NSB_PDL=0;NSB_L2_PERSIST_MB=48;NSB_L2_PERSIST_MB=80;NSB_L2_PERSIST_MB=112;NSB_L2_FETCH=32;NSB_L2_FETCH=128;NSB_PDL=1;NSB_PDL=1,NSB_L2_PERSIST_MB=80"
-for o in 2 1; do
-  NSB_VERBOSE=1 timeout 240 python scripts/prof_variants.py cyl3d-20M $o 5 "$V20" 2>&1 | tee gpurun_out/r2m_prof_20M_o$o.log
-done
+NSB_VERBOSE=1 timeout 240 python scripts/prof_variants.py cyl3d-20M 2 5 "$V20;NSB_BSELL_OCC=10;NSB_PDL=1,NSB_BSELL_OCC=10;NSB_PDL=1,NSB_BSELL_OCC=10,NSB_L2_PERSIST_MB=80" 2>&1 | tee gpurun_out/r2m_prof_20M_o2.log
+NSB_VERBOSE=1 timeout 240 python scripts/prof_variants.py cyl3d-20M 1 5 "$V20" 2>&1 | tee gpurun_out/r2m_prof_20M_o1.log
 timeout 240 python bench.py --workload cyl2d-2M --steps 4 --warmup 1 --no-cpu-baseline > gpurun_out/r2m_bench_cyl2d_2M.json 2> gpurun_out/r2m_bench_cyl2d_2M.err
 echo "cyl2d-2M rc=$?"; grep -E "^\[bench" gpurun_out/r2m_bench_cyl2d_2M.err | tail -5
