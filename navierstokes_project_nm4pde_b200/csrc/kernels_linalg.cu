@@ -1343,15 +1343,17 @@ static void trsv_levels(Handle &H, DevIlu &ilu, double *y, cudaStream_t s)
   }
 }
 
-// NSB_PDL (default off): chain the colour sweeps of a triangular solve by programmatic dependent launch
-// (nsb_internal.hpp).  Read when a solve is captured.
+// NSB_PDL (default on): chain the colour sweeps of a triangular solve by programmatic dependent launch
+// (nsb_internal.hpp).  Read when a solve is captured.  Measured (session M, profiles/README.md): ILU apply of the
+// pressure matrix 0.285 -> 0.186 ms at 2 M DoF and 0.51 -> 0.41 ms at 19.9 M; of F_s 0.289 -> 0.258 / 1.98 -> 1.89 ms.
 bool pdl_enabled()
 {
   const char *e = getenv("NSB_PDL");
-  return e ? atoi(e) != 0 : false; // off until measured on hardware
+  return e ? atoi(e) != 0 : true;
 }
 
-// NSB_L2_PERSIST_MB (default 0 = off): set aside that much of the L2 for persisting lines and mark the staging
+// NSB_L2_PERSIST_MB (default 0 = off; measured SLOWER in session M: F_s apply 1.98 -> 2.06 ms with 48 MB, 2.53 ms with
+// 79 MB set aside, and the SpMV loses the set-aside too -- kept as a knob for the record): set aside that much of the L2 for persisting lines and mark the staging
 // vector of the captured solve as persisting (hit ratio = set-aside / window): a colour sweep gathers rows that
 // OTHER colours wrote from the whole vector, which is larger than the L2 at 19.9 M DoF, so without a policy
 // every gather is a DRAM miss; with it a fixed subset of the vector stays resident across the sweeps.  The window is

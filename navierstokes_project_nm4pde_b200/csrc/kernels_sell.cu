@@ -356,10 +356,10 @@ __device__ __forceinline__ void bsell_gather(const double *yp, int c, double (&x
 
 // DIR 0: forward substitution  y = x - L y          (unit diagonal, Ifpack: L scaled by dinv_j)
 // DIR 1: backward substitution y = y * dinv - U y   (Ifpack: U scaled by dinv_i), also stored to io->y
-// MINB: resident CTAs per SM the register allocation aims at (8: 64 registers; 10: 51, no spills -- more warps to
-// hide the gather latency of a warp's serial passes; NSB_BSELL_OCC selects, see launch_bsell)
-template <int BS, int DIR, bool STAGE, int MINB = 8>
-__global__ void __launch_bounds__(kBW * 32, MINB) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
+// (8 CTAs per SM = 64 registers; a 48-register build for 10 CTAs per SM was measured slower: 2.13 ms against 1.98 ms
+// per apply at 19.9 M DoF, session M)
+template <int BS, int DIR, bool STAGE>
+__global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
                                                        const int *__restrict__ e_ptr, const unsigned *__restrict__ e_len,
                                                        const unsigned char *__restrict__ e_prow,
                                                        const unsigned short *__restrict__ e_lix,
@@ -637,9 +637,9 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
   if (need > size_t(48) * 1024) {
     const int lim = int(need);
     auto raise = [&](auto kernel) { NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); };
-    if (ilu.bs_rhs == 3) { raise(k_bsell<3, 0, false, 8>); raise(k_bsell<3, 1, false, 8>); raise(k_bsell<3, 0, false, 10>); raise(k_bsell<3, 1, false, 10>); }
-    else if (ilu.bs_rhs == 2) { raise(k_bsell<2, 0, false, 8>); raise(k_bsell<2, 1, false, 8>); raise(k_bsell<2, 0, false, 10>); raise(k_bsell<2, 1, false, 10>); }
-    else { raise(k_bsell<1, 0, true, 8>); raise(k_bsell<1, 1, true, 8>); raise(k_bsell<1, 0, true, 10>); raise(k_bsell<1, 1, true, 10>); }
+    if (ilu.bs_rhs == 3) { raise(k_bsell<3, 0, false>); raise(k_bsell<3, 1, false>); }
+    else if (ilu.bs_rhs == 2) { raise(k_bsell<2, 0, false>); raise(k_bsell<2, 1, false>); }
+    else { raise(k_bsell<1, 0, true>); raise(k_bsell<1, 1, true>); }
   }
 }
 
@@ -666,14 +666,9 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
   const int max_nx = STAGE ? B.col_max_nx[colour] : 0;
   const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
-  const char *occ = getenv("NSB_BSELL_OCC"); // read when a solve is captured
-  auto go = [&](auto kernel) {
-    launch_k(kernel, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_col.p,
-             B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p, ilu.order.p, io,
-             B.max_int, max_nx, int(wb));
-  };
-  if (occ && atoi(occ) == 10) go(k_bsell<BS, DIR, STAGE, 10>);
-  else go(k_bsell<BS, DIR, STAGE, 8>);
+  launch_k(k_bsell<BS, DIR, STAGE>, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p,
+           B.e_col.p, B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p,
+           ilu.order.p, io, B.max_int, max_nx, int(wb));
 }
 
 template <int BS>
