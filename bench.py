@@ -65,8 +65,16 @@ DELTAT = {"3d": 2e-4, "2d": 0.01}          # main3D.cpp:38, main2D.cpp:22
 PRECOND = {"3d": "yosida", "2d": "asimple"}  # NavierStokes3D.cpp:562, NavierStokes2D.cpp:547
 N_DOFS = {"cyl3d-20M": 19923035, "cyl3d-2M": 2059237, "cyl3d-500k": 530456}
 AUTO_BLOCK_MIN_DOFS = 1.5e7                  # --ilu-ordering -1: block multicolour ILU above this many DoF per GPU
-PREP_INNER_RTOL = 1e-4                      # inner tolerance of the two untimed start-up steps
+PREP_INNER_RTOL = 1e-4                      # inner tolerance of the two untimed start-up steps (3D only, see prep_rtol)
 PREP_STEPS = 2
+
+
+def prep_rtol(variant):
+    """Inner tolerance of the untimed start-up steps.  3D: tightened (the impulsive start from u = 0 otherwise costs
+    ~1 500 outer iterations).  2D: the reference's 1e-2 -- the inlet ramps up smoothly (test case 2) and the inner
+    GMRES(28) + ILU(0) on the Schur complement already needs thousands of iterations per solve at 2 M DoF
+    (tests/test_gpu_properties.py); a tighter tolerance would hit the reference's 10 000-iteration limit."""
+    return PREP_INNER_RTOL if variant == "3d" else 1e-2
 
 
 def make_mesh(workload):
@@ -192,7 +200,7 @@ def run_cpu(workload, steps, warmup, budget_s=None):
     o.set_dirichlet(prob._dir_rows, prob.dirichlet_values(tm))
     o.set_solution(np.zeros(d.N))
     ptype = PRECOND[variant]
-    o.set_options(inner_rtol=PREP_INNER_RTOL)
+    o.set_options(inner_rtol=prep_rtol(variant))
     o.assemble_first()
     o.solve_step(ptype)
     for _ in range(PREP_STEPS - 1):
@@ -268,7 +276,7 @@ class GpuRun:
         """u_0 = 0, then the PREP_STEPS start-up steps (tightened inner solves, reference outer tolerance)."""
         e = self.e
         e.set_solution(self.prob.initial_condition())
-        e.set_params(inner_rtol=PREP_INNER_RTOL)
+        e.set_params(inner_rtol=prep_rtol(self.variant))
         its = [self.step() for _ in range(PREP_STEPS)]
         e.set_params(inner_rtol=1e-2)  # Preconditioners.hpp:260
         return its
@@ -315,7 +323,7 @@ def run_gpu(args):
     barrier(); t0 = time.perf_counter()
     its_prep = run.prepare()
     barrier(); prep_s = time.perf_counter() - t0
-    log(f"start-up steps (inner rtol {PREP_INNER_RTOL:g}): {its_prep} outer iterations, {prep_s:.1f} s")
+    log(f"start-up steps (inner rtol {prep_rtol(run.variant):g}): {its_prep} outer iterations, {prep_s:.1f} s")
 
     warm_its, warm_s = [], []
     for _ in range(args.warmup):
@@ -401,7 +409,7 @@ def run_gpu(args):
                                               1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
                                      "timings flush L2 between launches",
-                           start_up=f"{PREP_STEPS} untimed steps from u=0 with inner rtol {PREP_INNER_RTOL:g}, then reference literals",
+                           start_up=f"{PREP_STEPS} untimed steps from u=0 with inner rtol {prep_rtol(variant):g}, then reference literals",
                            partition=f"{world} subdomain(s), coordinate bisection",
                            transport=(getattr(prob, "transport", "none") if world > 1 else "none")),
                e2e=e2e, roofline=roofline, clocks=clocks,

@@ -177,12 +177,14 @@ def test_midsize_parity_against_the_oracle():
 
 def test_2d_refined_cylinder_2M_properties():
     """BASELINE.json configs[3]: the globally refined 2D cylinder (~2 M DoF, `bench.py` workload `cyl2d-2M`,
-    NavierStokes2D + aSIMPLE with inner GMRES on the Schur complement, NavierStokes2D.cpp:547,
-    Preconditioners.hpp:254-311) through the 2D kernels at bench size: divergence of a constant field,
-    linearity and block composition of the system SpMV, the rhs / F.1 identity of assemble_time_step
-    (with the Temam term, which 2D keeps), the ILU(0) applies, one reference time step whose true
-    preconditioned residual has dropped to the inner tolerance, and drag / lift on the device against
-    the host face loop on the downloaded solution."""
+    NavierStokes2D + aSIMPLE, NavierStokes2D.cpp:547, Preconditioners.hpp:254-311) through the 2D kernels at
+    bench size: divergence of a constant field, linearity and block composition of the system SpMV, the
+    rhs / F.1 identity of assemble_time_step (with the Temam term, which 2D keeps), linearity of both ILU(0)
+    applies, and drag / lift on the device against the host face loop on the same field.  The time step itself is
+    checked against the oracle on the 0.16 M-DoF mesh of the same family (next test): at 2 M DoF the reference's
+    inner GMRES(28) + ILU(0) on the Schur complement needs thousands of iterations per solve -- on the CPU
+    restatement 314 per solve at 0.16 M DoF and 1 058 at 0.64 M (natural ordering) -- which is the reference
+    algorithm's own limit on this configuration (it throws NoConvergence at 10 000), not a property to assert on."""
     dt = bench.DELTAT["2d"]
     (s,) = bench.WORKLOADS["cyl2d-2M"][1]
     p = NavierStokes(HostMesh.cylinder2d(s), "2d", T=1.0, deltat=dt, test_case=2, ilu_ordering=1, orthogonalisation=1)
@@ -191,6 +193,7 @@ def test_2d_refined_cylinder_2M_properties():
     e, nu, rng = p.engine, p.n_u, np.random.default_rng(20240607)
     x0 = np.zeros(p.N)
     x0[:nu] = 0.1 * rng.uniform(-1.0, 1.0, nu)
+    x0[nu:] = rng.uniform(-1.0, 1.0, p.N - nu)
     e.set_solution(x0)
     e.set_dirichlet_values(p.dirichlet_values(2.0 + dt))
     e.assemble_first(dt)
@@ -205,6 +208,10 @@ def test_2d_refined_cylinder_2M_properties():
     assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
     yy = e.system_vmult(x)
     assert np.linalg.norm(yy[:nu] - e.block_vmult("F", x[:nu]) - e.block_vmult("Bt", x[nu:])) < 1e-13 * np.linalg.norm(yy[:nu])
+    # drag / lift: device kernel == host face loop on the same (rough) field
+    f_dev = e.compute_forces()
+    f_host = p.dofs.boundary_forces(x0, 3, p.nu, 1.0)
+    assert np.allclose(f_dev, f_host, rtol=1e-10, atol=1e-13 * np.abs(f_host).max())
     # constant advecting state: rhs = c (F 1) on unconstrained rows (Temam term vanishes for div c = 0)
     c = np.array([0.8, -0.4])
     xc = np.zeros(p.N)
@@ -216,21 +223,57 @@ def test_2d_refined_cylinder_2M_properties():
     m[p._dir_rows] = False
     expect = np.tile(c, nu // 2) * F1
     assert np.abs(e.get_rhs()[:nu][m] - expect[m]).max() < 1e-11 * np.abs(expect[m]).max()
-    # ILU(0) applies are linear
+    # ILU(0) applies are linear (velocity block and Schur complement, through the colour sweeps)
     e.precond_init()
-    xu, zu = rng.uniform(-1, 1, nu), rng.uniform(-1, 1, nu)
-    lhs = e.ilu_apply(0, 0.5 * xu - 3.0 * zu)
-    rhs = 0.5 * e.ilu_apply(0, xu) - 3.0 * e.ilu_apply(0, zu)
-    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
-    # one time step from the rough state
-    e.set_solution(x0)
-    e.assemble_step(2 * dt)
-    its, _, _ = e.solve_step()
-    assert its > 0 and e.stat("n_F_solves") == e.stat("n_S_solves") > 0  # aSIMPLE: one F and one Schur solve per vmult
-    xs, b = e.get_solution(), e.get_rhs()
-    zr, z0 = e.precond_vmult(b - e.system_vmult(xs)), e.precond_vmult(b)
+    for which, n in ((0, nu), (1, p.N - nu)):
+        xu, zu = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        lhs = e.ilu_apply(which, 0.5 * xu - 3.0 * zu)
+        rhs = 0.5 * e.ilu_apply(which, xu) - 3.0 * e.ilu_apply(which, zu)
+        assert np.isfinite(lhs).all() and np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(rhs)
+
+
+@pytest.mark.parametrize("ordering", [1, 2])
+def test_2d_midsize_time_step_against_the_oracle(ordering):
+    """0.16 M DoF (`cyl2d-160k`, the 2D mesh of bench.py's CPU legs): NavierStokes2D + aSIMPLE in the throughput
+    configuration against the oracle factorising in the engine's ILU order -- ILU applies and Schur product to
+    1e-10, then the reference's first time step.  Its inner GMRES on the Schur complement runs 300-500 iterations
+    per solve (restarted GMRES(28) close to stagnation), so iteration counts are compared with a margin and the
+    fields to the accuracy of the outer tolerance."""
+    import helpers as T
+    from oracle import ns_ref as R
+
+    dt = bench.DELTAT["2d"]
+    (s,) = bench.WORKLOADS["cyl2d-160k"][1]
+    mesh = HostMesh.cylinder2d(s)
+    p = NavierStokes(mesh, "2d", T=1.0, deltat=dt, test_case=2, ilu_ordering=ordering, orthogonalisation=1)
+    p.setup()
+    d, e = p.dofs, p.engine
+    num = dict(dim=2, cell_dofs=d.cell_dofs(), N=d.N, n_u=d.n_u, n_p=d.n_p, dpc=d.dpc)
+    o = R.Oracle(2, "2d", mesh.vertices, mesh.cells, num, R.system_pattern(num), 1e-3, dt)
+    ou = (2 * e.ilu_order(0)[:, None] + np.arange(2)[None, :]).ravel()
+    o.set_ilu_order(ou, e.ilu_order(1))
+    o.set_orthogonalisation(1)
+    vals = p.dirichlet_values(dt)
+    o.set_dirichlet(p._dir_rows, vals)
+    e.set_dirichlet_values(vals)
+    for side in (o, e):
+        side.set_solution(np.zeros(d.N))
+        side.assemble_first()
+    o.precond_init("asimple"); e.precond_init()
+    rng = np.random.default_rng(T.SEED)
+    x = rng.uniform(-1.0, 1.0, d.N)
+    xu, xp = x[: d.n_u], x[d.n_u:]
+    assert T.rel_l2(e.system_vmult(x), o.system_vmult(x)) < 1e-12
+    assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-10
+    assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-10
+    assert T.rel_l2(e.block_vmult("S", xp), o.block_vmult(3, xp, d.n_p)) < 1e-11
+    rc, its_o, _ = o.solve_step("asimple")
+    its_e, _, _ = e.solve_step()
+    assert rc == 0 and abs(its_e - its_o) <= max(3, its_o // 5), (its_e, its_o)
+    assert e.stat("n_F_solves") == e.stat("n_S_solves") > 0  # aSIMPLE: one F and one Schur solve per vmult
+    xe, xo = e.get_solution(), o.array("sol_owned", d.N)
+    assert T.rel_l2(xe[: d.n_u], xo[: d.n_u]) < 1e-3
+    # the true preconditioned residual of the engine's solution has dropped like the solver says
+    b = e.get_rhs()
+    zr, z0 = e.precond_vmult(b - e.system_vmult(xe)), e.precond_vmult(b)
     assert np.isfinite(zr).all() and np.linalg.norm(zr) < 5e-2 * np.linalg.norm(z0)
-    # drag / lift: device kernel == host face loop on the same field
-    f_dev = e.compute_forces()
-    f_host = p.dofs.boundary_forces(xs, 3, p.nu, 1.0)
-    assert np.allclose(f_dev, f_host, rtol=1e-10, atol=1e-13 * np.abs(f_host).max())
