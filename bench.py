@@ -245,9 +245,12 @@ class GpuRun:
             self.ilu_ordering = 2 if n_dofs / max(world, 1) >= AUTO_BLOCK_MIN_DOFS else 1
         else:
             self.ilu_ordering = args.ilu_ordering
+        # the pressure matrix keeps the point multicolour sweeps when F_s takes the block sweeps (session M: 0.41 ms
+        # against 0.83 ms per apply at 19.9 M DoF, same CG iteration count)
+        self.ilu_ordering_schur = args.ilu_ordering_schur if args.ilu_ordering_schur >= 0 else (1 if self.ilu_ordering == 2 else self.ilu_ordering)
         self.dt = DELTAT[self.variant]
         kw = dict(T=1.0, deltat=self.dt, test_case=2, device=local_rank, ilu_ordering=self.ilu_ordering,
-                  orthogonalisation=args.orthogonalisation)
+                  ilu_ordering_schur=self.ilu_ordering_schur, orthogonalisation=args.orthogonalisation)
         if world > 1:
             from navierstokes_project_nm4pde_b200.distributed import DistributedNavierStokes
 
@@ -318,7 +321,7 @@ def run_gpu(args):
     run = GpuRun(args.workload, args, world, rank, local_rank, uid[0])
     e, prob = run.e, run.prob
     setup_s = time.perf_counter() - t_setup
-    log(f"setup done: {args.workload}, {run.mesh.n_cells} cells, {run.n_dofs} DoF, ilu_ordering {run.ilu_ordering}, transport {getattr(prob, 'transport', 'none')}")
+    log(f"setup done: {args.workload}, {run.mesh.n_cells} cells, {run.n_dofs} DoF, ilu_ordering {run.ilu_ordering} / {run.ilu_ordering_schur} (F_s / Schur), transport {getattr(prob, 'transport', 'none')}")
 
     barrier(); t0 = time.perf_counter()
     its_prep = run.prepare()
@@ -405,6 +408,7 @@ def run_gpu(args):
                                          2: "block multicolour, natural order inside 32-row blocks (throughput mode)",
                                          3: "subdomain ordering: parts solved out of shared memory, separators last "
                                             "(throughput mode)"}[run.ilu_ordering],
+                           ilu_ordering_schur=int(run.ilu_ordering_schur),
                            orthogonalisation={0: "modified Gram-Schmidt (reference replay)",
                                               1: "batched classical Gram-Schmidt (throughput mode)"}[args.orthogonalisation],
                            l2_policy="working set (>1 GB of matrices) exceeds the 126 MB L2; isolated kernel "
@@ -475,6 +479,8 @@ def main():
                     help="0: natural row order (reference replay), 1: multicolour ILU(0), 2: block multicolour ILU(0), "
                          "3: subdomain-resident ILU(0) (throughput modes); -1 (default): 2 above 15 M DoF per GPU, else 1 "
                          "(measured: the block sweeps need large colours, profiles/README.md)")
+    ap.add_argument("--ilu-ordering-schur", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+                    help="ordering of the Schur-complement factors; -1 (default): 1 when F_s uses 2, else the same as F_s")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
     args = ap.parse_args()

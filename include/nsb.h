@@ -93,7 +93,12 @@ typedef struct nsb_params {
                               1: batched classical Gram-Schmidt (throughput mode): all coefficients of one
                               Arnoldi step from ONE fused multi-dot kernel and one all-reduce; inner solves
                               re-orthogonalise on deal.II's loss test, the outer solve always does two passes */
-  int32_t reserved[6];
+  int32_t ilu_ordering_schur; /* ordering of the Schur-complement factors: -1 (nsb_default_params): same as
+                              ilu_ordering; 0..3 as above.  The pressure matrix has one right-hand side and short
+                              colours, so its sweeps are latency-bound: at 19.9 M DoF the point multicolour sweeps
+                              (1) cost 0.41 ms per apply against 0.83 ms for the block sweeps (2) at the same CG
+                              iteration count, while F_s prefers 2 (fewer inner iterations).  Before nsb_finalize_setup. */
+  int32_t reserved[5];
 } nsb_params;
 
 /* Fill *p with the reference's literals for the given variant. */

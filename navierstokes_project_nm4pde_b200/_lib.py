@@ -21,7 +21,7 @@ class NsbParams(C.Structure):
         ("gmres_tmp", C.c_int32), ("outer_maxit", C.c_int32), ("outer_tol", C.c_double),
         ("inner_maxit", C.c_int32), ("inner_rtol", C.c_double), ("alpha_simple", C.c_double),
         ("alpha_asimple", C.c_double), ("dirichlet_mode", C.c_int32), ("assembly_kernel", C.c_int32),
-        ("sptrsv_kernel", C.c_int32), ("ilu_ordering", C.c_int32), ("orthogonalisation", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("sptrsv_kernel", C.c_int32), ("ilu_ordering", C.c_int32), ("orthogonalisation", C.c_int32), ("ilu_ordering_schur", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 

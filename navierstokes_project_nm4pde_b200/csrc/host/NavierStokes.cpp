@@ -230,6 +230,7 @@ void NavierStokes::setup()
   prm.deltat = deltat;
   prm.ilu_ordering = ilu_ordering;
   prm.orthogonalisation = orthogonalisation;
+  prm.ilu_ordering_schur = ilu_ordering_schur;
   check(nsb_set_params(engine, &prm), "nsb_set_params");
   check(nsb_set_mesh(engine, n_cells, cell_coords, cell_dofs, n_u, n_p, dim * n_nodes_owned, n_p_owned), "nsb_set_mesh");
   const Rule q = gauss_simplex(dim); // QGaussSimplex<dim>(fe->degree + 1), NavierStokes2D.cpp:45

@@ -56,6 +56,7 @@ public:
   int max_steps = -1;        // stop after this many steps (reference: run to T)
   int ilu_ordering = 0;      // 0: reference replay, 1 / 2 / 3: throughput orderings (nsb_params)
   int orthogonalisation = 0; // 0: modified Gram-Schmidt as SolverGMRES, 1: batched (throughput mode)
+  int ilu_ordering_schur = -1; // ordering of the Schur-complement factors (-1: same as ilu_ordering)
   int device = 0;
   double forces_after = 0.1; // NavierStokes3D.cpp:728 computes forces only for time > 0.1
   bool write_output = false; // VTU per step (2D) / every 20 steps (3D), gmres.csv, coeff_2.csv as the reference

@@ -4,7 +4,7 @@
 //   NSB_MAX_STEPS=<n>   stop after n time steps      NSB_T=<T>  final time
 //   NSB_ILU_ORDERING=1  multicolour ILU(0) (throughput mode)     NSB_DEVICE=<id>
 //   NSB_OUTPUT=1        write the reference's side outputs (.vtu, gmres.csv, coeff_2.csv); off by default
-//   NSB_ORTHOGONALISATION=1  batched Gram-Schmidt (throughput mode)
+//   NSB_ORTHOGONALISATION=1  batched Gram-Schmidt (throughput mode)   NSB_ILU_ORDERING_SCHUR=<k>  Schur factors' ordering
 // One process per GPU (the reference under mpirun): start the binary N times with RANK / WORLD_SIZE /
 // LOCAL_RANK / MASTER_ADDR set -- `python -m torch.distributed.run --no-python --nproc-per-node N <binary> <mesh>`
 // or scripts/nsb_launch.sh -- see rendezvous.hpp.  NSB_P2P=0 keeps NCCL instead of peer memory.
@@ -75,6 +75,7 @@ inline void apply_env(NavierStokes &problem, Utilities::MPI::MPI_InitFinalize &m
   problem.max_steps = env_int("NSB_MAX_STEPS", -1);
   problem.ilu_ordering = env_int("NSB_ILU_ORDERING", 0);
   problem.orthogonalisation = env_int("NSB_ORTHOGONALISATION", 0);
+  problem.ilu_ordering_schur = env_int("NSB_ILU_ORDERING_SCHUR", -1);
   problem.device = env_int("NSB_DEVICE", comm.local_rank());
   problem.forces_after = env_double("NSB_FORCES_AFTER", 0.1);
   problem.write_output = env_int("NSB_OUTPUT", 0) != 0;

@@ -77,6 +77,7 @@ extern "C" int nsb_default_params(nsb_params *p, int variant)
   p->inner_rtol = 1e-2;
   p->alpha_simple = 0.5;
   p->alpha_asimple = 1.0;
+  p->ilu_ordering_schur = -1; // same as ilu_ordering
   return NSB_OK;
 }
 
@@ -154,7 +155,9 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
     if (p->ilu_ordering < 0 || p->ilu_ordering > 3) throw ArgError("nsb_set_params: ilu_ordering must be 0, 1, 2 or 3");
     if (p->orthogonalisation < 0 || p->orthogonalisation > 1)
       throw ArgError("nsb_set_params: orthogonalisation must be 0 or 1");
-    if (H.finalized && p->ilu_ordering != H.prm.ilu_ordering)
+    if (p->ilu_ordering_schur < -1 || p->ilu_ordering_schur > 3)
+      throw ArgError("nsb_set_params: ilu_ordering_schur must be -1 (same as ilu_ordering), 0, 1, 2 or 3");
+    if (H.finalized && (p->ilu_ordering != H.prm.ilu_ordering || p->ilu_ordering_schur != H.prm.ilu_ordering_schur))
       throw StateError("nsb_set_params: ilu_ordering must be chosen before nsb_finalize_setup");
     if (!(p->deltat > 0) || !(p->nu > 0)) throw ArgError("nsb_set_params: nu and deltat must be positive");
     const bool realloc_ws = H.finalized && p->gmres_tmp != H.prm.gmres_tmp;
@@ -346,7 +349,8 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     H.sellF_dirty = true;
     phase("SpMV formats (SELL, stream)");
     std::vector<double> xyz_n, xyz_p; // support points of the P2 nodes / pressure vertices (subdomain ordering)
-    if (H.prm.ilu_ordering == 3) {
+    const int ord_s = H.prm.ilu_ordering_schur < 0 ? H.prm.ilu_ordering : H.prm.ilu_ordering_schur;
+    if (H.prm.ilu_ordering == 3 || ord_s == 3) {
       xyz_n.assign(size_t(H.n_nodes) * dim, 0.0);
       xyz_p.assign(size_t(H.n_p) * dim, 0.0);
       for (int64_t c = 0; c < nc; ++c) {
@@ -362,7 +366,7 @@ extern "C" int nsb_finalize_setup(nsb_handle h)
     }
     ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering, xyz_n.empty() ? nullptr : xyz_n.data(), dim);
     phase("ILU schedule F");
-    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, H.prm.ilu_ordering, xyz_p.empty() ? nullptr : xyz_p.data(), dim);
+    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, ord_s, xyz_p.empty() ? nullptr : xyz_p.data(), dim);
     phase("ILU schedule S");
     solver_alloc(H);
     NSB_CUDA(cudaDeviceSynchronize());

@@ -328,6 +328,53 @@ def test_multicolour_ilu_mode(case_name, ptype, ordering, monkeypatch):
     assert e.stat("sweeps_F") <= 40 and e.stat("sweeps_S") <= 80
 
 
+@pytest.mark.parametrize("case_name,ptype,ord_f,ord_s", [("cyl3d", "yosida", 2, 1), ("cyl2d", "asimple", 2, 1),
+                                                         ("box3d", "yosida", 1, 0), ("cube", "yosida", 2, 1)])
+def test_separate_ordering_of_the_schur_factors(case_name, ptype, ord_f, ord_s):
+    """nsb_params.ilu_ordering_schur: the Schur-complement factors in a different elimination order than F_s
+    (bench.py at 19.9 M DoF: block multicolour for F_s, point multicolour for the pressure matrix); the oracle
+    factorises each matrix in the order the engine reports.  Batched Gram-Schmidt as in the bench."""
+    case = T.Case(case_name)
+    o = case.oracle()
+    e = case.engine(precond_type=ptype, ilu_ordering=ord_f, ilu_ordering_schur=ord_s, orthogonalisation=1)
+    ref = case.engine(precond_type=ptype, ilu_ordering=ord_s, orthogonalisation=1)
+    assert np.array_equal(e.ilu_order(1), ref.ilu_order(1))  # the pressure ordering is the one asked for
+    if ord_f != ord_s:
+        assert not np.array_equal(e.ilu_order(0), ref.ilu_order(0))
+    del ref
+    o.set_ilu_order(*_oracle_order(case, e))
+    o.set_orthogonalisation(1)
+    rows, vals = case.bc(0.0)
+    o.set_dirichlet(rows, vals)
+    e.set_dirichlet(rows)
+    x0 = case.initial()
+    o.set_solution(x0)
+    e.set_solution(x0)
+    t = 0.0
+    for step in range(2):
+        t += case.dt
+        rows, vals = case.bc(t if case.variant == "conv" else 2.0 + t)
+        o.set_dirichlet_values(vals)
+        e.set_dirichlet_values(vals)
+        if case.variant == "conv":
+            neu = case.neumann(t - case.dt)
+            o.set_neumann_rhs(neu)
+            e.set_neumann_rhs(neu[: case.n_u])
+        if step == 0:
+            o.assemble_first(); e.assemble_first()
+            o.precond_init(ptype); e.precond_init()
+            x = case.random_state()
+            xu, xp = x[: case.n_u], x[case.n_u:]
+            assert T.rel_l2(e.ilu_apply(0, xu), o.ilu_apply(0, xu)) < 1e-11
+            assert T.rel_l2(e.ilu_apply(1, xp), o.ilu_apply(1, xp)) < 1e-11
+        else:
+            o.assemble_step(); e.assemble_step()
+        rc, its_o, _ = o.solve_step(ptype)
+        its_e, _, _ = e.solve_step()
+        assert rc == 0 and its_e == its_o, (step, its_e, its_o)
+        assert T.rel_l2(e.get_solution()[: case.n_u], o.array("sol_owned", case.N)[: case.n_u]) < FIELD_TOL, step
+
+
 @pytest.mark.parametrize("ordering", [1, 2])
 @pytest.mark.parametrize("case_name,ptype", [("cyl2d", "asimple"), ("box3d", "yosida"), ("cyl3d", "yosida"),
                                              ("cube", "yosida")])
