@@ -60,7 +60,8 @@ UNIT = "DoF-timesteps/s"
 # (refined 2D cylinder, ~2 M DoF, NavierStokes2D + aSIMPLE, main2D.cpp:21-22).
 WORKLOADS = {"cyl3d-20M": ("3d", (8, 40)), "cyl3d-16M": ("3d", (8, 32)), "cyl3d-2M": ("3d", (4, 16)),
              "cyl3d-900k": ("3d", (3, 12)), "cyl3d-500k": ("3d", (3, 7)), "cyl3d-270k": ("3d", (2, 8)),
-             "cyl3d-30k": ("3d", (1, 3)), "cyl2d-2M": ("2d", (28,)), "cyl2d-160k": ("2d", (8,)), "cyl2d-3k": ("2d", (1,))}
+             "cyl3d-30k": ("3d", (1, 3)), "cyl2d-2M": ("2d", (28,)), "cyl2d-640k": ("2d", (16,)), "cyl2d-160k": ("2d", (8,)),
+             "cyl2d-3k": ("2d", (1,))}
 DELTAT = {"3d": 2e-4, "2d": 0.01}          # main3D.cpp:38, main2D.cpp:22
 PRECOND = {"3d": "yosida", "2d": "asimple"}  # NavierStokes3D.cpp:562, NavierStokes2D.cpp:547
 N_DOFS = {"cyl3d-20M": 19923035, "cyl3d-2M": 2059237, "cyl3d-500k": 530456}

@@ -32,6 +32,9 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
   asm volatile("{ .reg .f64 pad; ld.global.v4.f64 {%0,%1,%2,pad}, [%3]; }" : "=d"(a), "=d"(b), "=d"(c) : "l"(p));
 }
 
+// line towards L2 without binding a value (L2 is the point of coherence: safe before pdl_wait())
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // in / out vectors of a captured triangular solve: the graph bakes kernel arguments, so the
 // caller's pointers are passed through this device-resident slot (set by k_set_io before launch)
 struct TrsvIo { const double *x; double *y; };
@@ -331,6 +334,13 @@ static int bsell_xcap()
   return e ? std::max(0, atoi(e)) : 1024;
 }
 
+// NSB_BSELL_PREFETCH (read when a solve is captured): software prefetch of a block's gathers into L2
+static int bsell_prefetch()
+{
+  const char *e = getenv("NSB_BSELL_PREFETCH");
+  return e ? atoi(e) : 0;
+}
+
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
 
 static size_t bsell_warp_bytes(int bs, int max_int, int max_nx)
@@ -371,7 +381,8 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
                                                        const double *__restrict__ i_val,
                                                        const unsigned *__restrict__ i_mask, double *yp,
                                                        const double *__restrict__ dinv, const int *__restrict__ order,
-                                                       const TrsvIo *__restrict__ io, int max_int, int max_nx, int warp_bytes)
+                                                       const TrsvIo *__restrict__ io, int max_int, int max_nx, int warp_bytes,
+                                                       int prefetch)
 {
   constexpr int PS = BS == 3 ? 4 : BS;
   constexpr unsigned FULL = 0xffffffffu;
@@ -414,6 +425,24 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   const unsigned lens = e_len[b];
   const int eb = e_ptr[b];
   const int xb = STAGE ? x_ptr[b] : 0, nx = STAGE ? min(x_ptr[b + 1] - xb, max_nx) : 0;
+  // ---- software prefetch: a warp walks its passes serially, each pass a dependent (col, val) -> gather round trip
+  // to DRAM.  All the block's column indices are read once here and the rows they name -- and the value stream --
+  // are requested into L2, so the passes below find their operands there.  L2 is the point of coherence, so this
+  // is legal before pdl_wait(): rows the previous colour is still writing are simply updated in place.
+  if (prefetch) {
+    const int tot = int(lens & 255u) + int((lens >> 8) & 255u) + int((lens >> 16) & 255u) + int(lens >> 24);
+    if (STAGE) {
+      for (int k = lane; k < nx; k += 32) prefetch_l2(yp + int64_t(PS) * x_ids[xb + k]);
+    } else {
+      const int *gp0 = e_col + eb + lane;
+#pragma unroll 4
+      for (int k = 0; k < tot; ++k) prefetch_l2(yp + int64_t(PS) * __ldg(gp0 + k * 32));
+    }
+    if ((lane & 15) == 0) { // the value stream: 256 B per step, one request per 128-B line
+      const double *vp0 = e_val + eb + lane;
+      for (int k = 0; k < tot; ++k) prefetch_l2(vp0 + k * 32);
+    }
+  }
   pdl_wait(); // the staging vector yp is read only from here on
   if (DIR == 1 && valid) {
     const double *yi = yp + int64_t(PS) * row;
@@ -668,7 +697,7 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
   launch_k(k_bsell<BS, DIR, STAGE>, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p,
            B.e_col.p, B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p,
-           ilu.order.p, io, B.max_int, max_nx, int(wb));
+           ilu.order.p, io, B.max_int, max_nx, int(wb), bsell_prefetch());
 }
 
 template <int BS>
