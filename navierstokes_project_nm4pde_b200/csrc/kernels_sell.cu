@@ -343,6 +343,13 @@ static int bsell_prefetch()
   return e ? atoi(e) : 1;
 }
 
+// NSB_BSELL_PIPE (read when a solve is captured): the software-pipelined walk over the four passes (k_bsell<.., PIPE>)
+static int bsell_pipe()
+{
+  const char *e = getenv("NSB_BSELL_PIPE");
+  return e ? atoi(e) : 0;
+}
+
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
 
 static size_t bsell_warp_bytes(int bs, int max_int, int max_nx)
@@ -370,7 +377,29 @@ __device__ __forceinline__ void bsell_gather(const double *yp, int c, double (&x
 // DIR 1: backward substitution y = y * dinv - U y   (Ifpack: U scaled by dinv_i), also stored to io->y
 // (8 CTAs per SM = 64 registers; a 48-register build for 10 CTAs per SM was measured slower: 2.13 ms against 1.98 ms
 // per apply at 19.9 M DoF, session M)
-template <int BS, int DIR, bool STAGE>
+// PIPE: the entries coupling with other blocks are walked as ONE software-pipelined stream over the four passes
+// (the (col, val) loads of the next four steps are in flight while the current four gathers are, and the first four
+// are issued before pdl_wait()) instead of pass by pass: ncu (session P, profiles/r02) shows the pass-by-pass version
+// waiting on a dependent (col, val) -> gather round trip per pass -- ~12 dependent round trips and 22 us per block,
+// long-scoreboard stalls 12.8 per issued instruction at 43 % occupancy.
+template <int BS>
+__device__ __forceinline__ void bsell_flush(double (&a)[BS], double *acc, int prow, int q, int lane)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1)
+#pragma unroll
+    for (int d = 0; d < BS; ++d) a[d] += __shfl_xor_sync(FULL, a[d], o);
+  const int lr = __shfl_sync(FULL, prow, q * 8 + (lane >> 2)); // local row of (pass q, slot lane / 4)
+  if ((lane & 3) == 0) { // every local row sits in exactly one (pass, slot): acc needs no clearing
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[lr * BS + d] = a[d];
+  }
+#pragma unroll
+  for (int d = 0; d < BS; ++d) a[d] = 0.0;
+}
+
+template <int BS, int DIR, bool STAGE, bool PIPE = false>
 __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int *__restrict__ blk_row,
                                                        const int *__restrict__ e_ptr, const unsigned *__restrict__ e_len,
                                                        const unsigned char *__restrict__ e_prow,
@@ -445,6 +474,21 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
       for (int k = 0; k < tot; ++k) prefetch_l2(vp0 + k * 32);
     }
   }
+  // PIPE: first stage of the (col, val) pipeline and the block's (pass, slot) -> local row table, before the wait
+  constexpr int U = 4;
+  const int tot_ext = int(lens & 255u) + int((lens >> 8) & 255u) + int((lens >> 16) & 255u) + int(lens >> 24);
+  [[maybe_unused]] int pc[U];
+  [[maybe_unused]] double pv[U];
+  [[maybe_unused]] int prow = 0;
+  if constexpr (PIPE) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = u < tot_ext;
+      pc[u] = ok ? (STAGE ? int(__ldcs(e_lix + eb + lane + u * 32)) : __ldcs(e_col + eb + lane + u * 32)) : 0;
+      pv[u] = ok ? __ldcs(e_val + eb + lane + u * 32) : 0.0;
+    }
+    prow = int(e_prow[size_t(b) * 32 + lane]);
+  }
   pdl_wait(); // the staging vector yp is read only from here on
   if (DIR == 1 && valid) {
     const double *yi = yp + int64_t(PS) * row;
@@ -463,7 +507,63 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   }
   __syncwarp();
   // ---- entries coupling with other blocks: four passes of eight rows, four lanes per row
-  {
+  if constexpr (PIPE) {
+    const unsigned short *cp = e_lix + eb + lane;
+    const int *gp = e_col + eb + lane;
+    const double *vp = e_val + eb + lane;
+    double a[BS];
+#pragma unroll
+    for (int d = 0; d < BS; ++d) a[d] = 0.0;
+    int q = 0, bound = int(lens & 255u); // bound: step after the last one of pass q (cumulative)
+    while (q < 4 && bound == 0) { // leading empty passes
+      bsell_flush<BS>(a, acc, prow, q, lane);
+      ++q;
+      bound += q < 4 ? int((lens >> (8 * q)) & 255u) : 0;
+    }
+    for (int k0 = 0; k0 < tot_ext; k0 += U) {
+      int nc[U];
+      double nv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { // next stage of the pipeline
+        const int kk = k0 + U + u;
+        const bool ok = kk < tot_ext;
+        nc[u] = ok ? (STAGE ? int(__ldcs(cp + kk * 32)) : __ldcs(gp + kk * 32)) : 0;
+        nv[u] = ok ? __ldcs(vp + kk * 32) : 0.0;
+      }
+      double x[U][BS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { // the gathers of this stage, all in flight together
+        if (k0 + u < tot_ext) {
+          if (STAGE && pc[u] < max_nx) {
+#pragma unroll
+            for (int d = 0; d < BS; ++d) x[u][d] = xs[pc[u] * BS + d];
+          } else
+            bsell_gather<BS>(yp, STAGE ? __ldcs(gp + (k0 + u) * 32) : pc[u], x[u]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < BS; ++d) x[u][d] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u < tot_ext) { // warp-uniform
+#pragma unroll
+          for (int d = 0; d < BS; ++d) a[d] += pv[u] * x[u][d];
+          while (q < 4 && k0 + u + 1 == bound) { // end of pass q (and of the empty passes that follow it)
+            bsell_flush<BS>(a, acc, prow, q, lane);
+            ++q;
+            bound += q < 4 ? int((lens >> (8 * q)) & 255u) : 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { pc[u] = nc[u]; pv[u] = nv[u]; }
+    }
+    while (q < 4) { // trailing empty passes (or a block without outside entries)
+      bsell_flush<BS>(a, acc, prow, q, lane);
+      ++q;
+    }
+  } else {
     const unsigned short *cp = e_lix + eb + lane;
     const int *gp = e_col + eb + lane;
     const double *vp = e_val + eb + lane;
@@ -668,9 +768,9 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
   if (need > size_t(48) * 1024) {
     const int lim = int(need);
     auto raise = [&](auto kernel) { NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); };
-    if (ilu.bs_rhs == 3) { raise(k_bsell<3, 0, false>); raise(k_bsell<3, 1, false>); }
-    else if (ilu.bs_rhs == 2) { raise(k_bsell<2, 0, false>); raise(k_bsell<2, 1, false>); }
-    else { raise(k_bsell<1, 0, true>); raise(k_bsell<1, 1, true>); }
+    if (ilu.bs_rhs == 3) { raise(k_bsell<3, 0, false, false>); raise(k_bsell<3, 1, false, false>); raise(k_bsell<3, 0, false, true>); raise(k_bsell<3, 1, false, true>); }
+    else if (ilu.bs_rhs == 2) { raise(k_bsell<2, 0, false, false>); raise(k_bsell<2, 1, false, false>); raise(k_bsell<2, 0, false, true>); raise(k_bsell<2, 1, false, true>); }
+    else { raise(k_bsell<1, 0, true, false>); raise(k_bsell<1, 1, true, false>); raise(k_bsell<1, 0, true, true>); raise(k_bsell<1, 1, true, true>); }
   }
 }
 
@@ -697,9 +797,13 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
   const int max_nx = STAGE ? B.col_max_nx[colour] : 0;
   const size_t wb = bsell_warp_bytes(BS, B.max_int, max_nx);
   const unsigned grid = unsigned((b1 - b0 + kBW - 1) / kBW);
-  launch_k(k_bsell<BS, DIR, STAGE>, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p,
-           B.e_col.p, B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p,
-           ilu.order.p, io, B.max_int, max_nx, int(wb), bsell_prefetch());
+  auto go = [&](auto kernel) {
+    launch_k(kernel, grid, kBW * 32, wb * kBW, s, pdl, b0, b1, ilu.blk_row.p, B.e_ptr.p, B.e_len.p, B.e_prow.p, B.e_lix.p, B.e_col.p,
+             B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p, ilu.order.p, io,
+             B.max_int, max_nx, int(wb), bsell_prefetch());
+  };
+  if (bsell_pipe()) go(k_bsell<BS, DIR, STAGE, true>);
+  else go(k_bsell<BS, DIR, STAGE, false>);
 }
 
 template <int BS>

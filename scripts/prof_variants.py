@@ -13,7 +13,7 @@ from navierstokes_project_nm4pde_b200 import HostMesh, NavierStokes
 
 wl, order, iters = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 variants = [v for v in sys.argv[4].split(";")] if len(sys.argv) > 4 else [""]
-KNOBS = ("NSB_PDL", "NSB_L2_PERSIST_MB", "NSB_L2_FETCH", "NSB_BSELL_PREFETCH")
+KNOBS = ("NSB_PDL", "NSB_L2_PERSIST_MB", "NSB_L2_FETCH", "NSB_BSELL_PREFETCH", "NSB_BSELL_PIPE")
 s, nz = bench.WORKLOADS[wl][1]
 prob = NavierStokes(HostMesh.cylinder3d(s, nz), "3d", T=1.0, deltat=bench.DELTAT["3d"], test_case=2, ilu_ordering=order)
 prob.setup()
