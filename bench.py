@@ -248,7 +248,15 @@ class GpuRun:
             self.ilu_ordering = args.ilu_ordering
         # the pressure matrix keeps the point multicolour sweeps when F_s takes the block sweeps (session M: 0.41 ms
         # against 0.83 ms per apply at 19.9 M DoF, same CG iteration count)
-        self.ilu_ordering_schur = args.ilu_ordering_schur if args.ilu_ordering_schur >= 0 else (1 if self.ilu_ordering == 2 else self.ilu_ordering)
+        # 2D (aSIMPLE: restarted GMRES on the Schur complement, hundreds to thousands of iterations per solve): the block
+        # ordering, whose ILU(0) is as good as the natural one -- with the point multicolour factors the inner GMRES hits
+        # the reference's 10 000-iteration limit from 0.64 M DoF on (sessions M-P)
+        if args.ilu_ordering_schur >= 0:
+            self.ilu_ordering_schur = args.ilu_ordering_schur
+        elif self.variant == "2d":
+            self.ilu_ordering_schur = 2
+        else:
+            self.ilu_ordering_schur = 1 if self.ilu_ordering == 2 else self.ilu_ordering
         self.dt = DELTAT[self.variant]
         kw = dict(T=1.0, deltat=self.dt, test_case=2, device=local_rank, ilu_ordering=self.ilu_ordering,
                   ilu_ordering_schur=self.ilu_ordering_schur, orthogonalisation=args.orthogonalisation)
@@ -481,7 +489,7 @@ def main():
                          "3: subdomain-resident ILU(0) (throughput modes); -1 (default): 2 above 15 M DoF per GPU, else 1 "
                          "(measured: the block sweeps need large colours, profiles/README.md)")
     ap.add_argument("--ilu-ordering-schur", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
-                    help="ordering of the Schur-complement factors; -1 (default): 1 when F_s uses 2, else the same as F_s")
+                    help="ordering of the Schur-complement factors; -1 (default): 2 in 2D, 1 in 3D when F_s uses 2, else the same as F_s")
     ap.add_argument("--orthogonalisation", type=int, default=1, choices=[0, 1],
                     help="0: modified Gram-Schmidt as deal.II (reference replay), 1: batched classical Gram-Schmidt")
     args = ap.parse_args()

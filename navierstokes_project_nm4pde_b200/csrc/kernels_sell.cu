@@ -343,11 +343,14 @@ static int bsell_prefetch()
   return e ? atoi(e) : 1;
 }
 
-// NSB_BSELL_PIPE (read when a solve is captured): the software-pipelined walk over the four passes (k_bsell<.., PIPE>)
-static int bsell_pipe()
+// NSB_BSELL_PIPE (read when a solve is captured): the software-pipelined walk over the four passes (k_bsell<.., PIPE>).
+// Default: on for one right-hand side (the pressure matrix: 0.673 -> 0.509 ms per apply at 19.9 M DoF, 0.551 -> 0.382 ms
+// at 2 M, session Q), off for the 3-component velocity block, where the deeper pipeline spills at 64 registers and
+// measured slower (1.867 -> 2.152 ms).
+static int bsell_pipe(int bs)
 {
   const char *e = getenv("NSB_BSELL_PIPE");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : (bs == 1 ? 1 : 0);
 }
 
 int bsell_stride(int bs_rhs) { return bs_rhs == 3 ? 4 : bs_rhs; }
@@ -802,7 +805,7 @@ static void launch_bsell(cudaStream_t s, const DevIlu &ilu, const DevBsell &B, i
              B.e_val.p, B.x_ptr.p, B.x_ids.p, B.i_ptr.p, B.i_off.p, B.i_col.p, B.i_val.p, B.i_mask.p, yp, ilu.dinv.p, ilu.order.p, io,
              B.max_int, max_nx, int(wb), bsell_prefetch());
   };
-  if (bsell_pipe()) go(k_bsell<BS, DIR, STAGE, true>);
+  if (bsell_pipe(BS)) go(k_bsell<BS, DIR, STAGE, true>);
   else go(k_bsell<BS, DIR, STAGE, false>);
 }
 
