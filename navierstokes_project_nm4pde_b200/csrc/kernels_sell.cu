@@ -345,8 +345,8 @@ static int bsell_prefetch()
 
 // NSB_BSELL_PIPE (read when a solve is captured): the software-pipelined walk over the four passes (k_bsell<.., PIPE>).
 // Default: on for one right-hand side (the pressure matrix: 0.673 -> 0.509 ms per apply at 19.9 M DoF, 0.551 -> 0.382 ms
-// at 2 M, session Q), off for the 3-component velocity block, where the deeper pipeline spills at 64 registers and
-// measured slower (1.867 -> 2.152 ms).
+// at 2 M, session Q), off for the 3-component velocity block, where it measured slower both at 64 registers with
+// spills (1.867 -> 2.152 ms) and at 80 registers / 6 CTAs per SM without (1.855 -> 2.082 ms, session T).
 static int bsell_pipe(int bs)
 {
   const char *e = getenv("NSB_BSELL_PIPE");
