@@ -23,10 +23,15 @@
  *   - Ifpack_ILU level 0 (inverse diagonal stored, U scaled by it), overlap 0
  *   - EpetraExt MatrixMatrix::Multiply as used by SparseMatrix::mmult(C, B, V)
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- *  and cannot be built here, so this oracle is pinned only by
- * pins created in this repo (sympy-exact element matrices, patch tests, convergence
- * orders; see tests/).
+ * PARITY UNPINNED with respect to the reference's own outputs: it ships no tests, golden
+ * vectors or fixtures and cannot be built here.  What pins
+ * this oracle instead:
+ *   - the published reference intervals of the DFG benchmark 2D-3 (Schaefer & Turek 1996),
+ *     which the reference's 2D driver with its own literals implements: the full 800-step
+ *     run of this file gives c_D,max = 2.932 at t = 3.94 on a 41 k-DoF mesh against
+ *     [2.93, 2.97] at t = 3.93 (tests/golden/make_dfg2d3.py, tests/test_golden.py);
+ *   - pins created in this repo (sympy-exact element matrices, patch tests, ILU(0) and Schur
+ *     product against dense / scipy references, convergence orders; tests/test_oracle_pins.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this file.  The product path never does.
