@@ -1398,7 +1398,11 @@ void ilu_reset_graphs(Handle &H)
     if (ilu->graph_f) { cudaGraphExecDestroy(ilu->graph_f); ilu->graph_f = nullptr; }
     if (ilu->graph_x) { cudaFree(ilu->graph_x); ilu->graph_x = nullptr; }
   }
-  // device-wide L2 knobs follow the environment of the next capture (profiling: scripts/prof_variants.py)
+  // device-wide L2 knobs follow the environment of the next capture (profiling: scripts/prof_variants.py); a
+  // process that never sets them never touches the device-wide limits
+  static bool l2_knobs_used = false;
+  if (!l2_knobs_used && !getenv("NSB_L2_FETCH") && !getenv("NSB_L2_PERSIST_MB")) return;
+  l2_knobs_used = true;
   static size_t fetch_default = 0;
   if (!fetch_default && cudaDeviceGetLimit(&fetch_default, cudaLimitMaxL2FetchGranularity) != cudaSuccess) fetch_default = 0;
   const char *e = getenv("NSB_L2_FETCH"); // hint: DRAM -> L2 fetch granularity in bytes (32 / 64 / 128)
