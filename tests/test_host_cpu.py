@@ -13,6 +13,7 @@ from navierstokes_project_nm4pde_b200 import Engine, HostDofs, HostMesh, NavierS
 from oracle import ns_ref as R
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R_SEED = 20240607
 
 
 def test_library_exports_every_declared_symbol():
@@ -296,3 +297,35 @@ def test_driver_rendezvous_without_gpu(tmp_path):
     assert "rendezvous ok: rank 0 of 3" in r.stdout
     for k in (1, 2):
         assert f"rendezvous ok: rank {k} of 3" in (tmp_path / f"rank{k}.log").read_text()
+
+
+@pytest.mark.parametrize("gen", [lambda: HostMesh.cylinder2d(1), lambda: HostMesh.cylinder3d(1, 3)])
+def test_find_cell_matches_point_value(gen):
+    """nsh_dofs_find_cell (the cell VectorTools::point_value evaluates in; lets one rank of a multi-rank run evaluate
+    only points of cells it owns): barycentric coordinates reproduce the point, a linear field is interpolated exactly
+    from them, points inside the obstacle / outside the channel are reported as -1."""
+    m = gen()
+    d = HostDofs(m)
+    dim = m.dim
+    L = _lib.lib()
+    rng = np.random.default_rng(R_SEED)
+    cc = d.cell_coords()
+    cells = rng.integers(0, d.n_cells, 20)
+    for c in cells:
+        w = rng.uniform(0.05, 1.0, dim + 1)
+        w /= w.sum()
+        x = np.ascontiguousarray(w @ cc[c])
+        lam = np.zeros(4)
+        k = L.nsh_dofs_find_cell(d.h, _lib.dptr(x), _lib.dptr(lam))
+        assert k >= 0
+        assert np.allclose(lam[: dim + 1] @ cc[k], x, atol=1e-12) and lam[: dim + 1].min() >= -1e-10
+        # a linear pressure field p = 1 + a.x through point_value
+        a = np.arange(1, dim + 1, dtype=float)
+        sol = np.zeros(d.N)
+        sol[d.n_u:] = 1.0 + d.p_xyz @ a
+        assert abs(d.point_value(sol, x)[dim] - (1.0 + x @ a)) < 1e-12
+    inside_obstacle = np.array([0.2, 0.2, 0.2][:dim]) if dim == 2 else np.array([0.5, 0.2, 0.2])
+    for x in (inside_obstacle, np.full(dim, -1.0)):
+        lam = np.zeros(4)
+        assert L.nsh_dofs_find_cell(d.h, _lib.dptr(np.ascontiguousarray(x)), _lib.dptr(lam)) == -1
+        assert d.point_value(np.zeros(d.N), x) is None
