@@ -28,8 +28,8 @@
  * this oracle instead:
  *   - the published reference intervals of the DFG benchmark 2D-3 (Schaefer & Turek 1996),
  *     which the reference's 2D driver with its own literals implements: the full 800-step
- *     run of this file gives c_D,max = 2.932 at t = 3.94 on a 41 k-DoF mesh against
- *     [2.93, 2.97] at t = 3.93 (tests/golden/make_dfg2d3.py, tests/test_golden.py);
+ *     run of this file gives c_D,max = 2.932 / 2.943 at t = 3.94 on 41 k / 91 k-DoF meshes
+ *     against [2.93, 2.97] at t = 3.93 (tests/golden/make_dfg2d3.py, tests/test_golden.py);
  *   - pins created in this repo (sympy-exact element matrices, patch tests, ILU(0) and Schur
  *     product against dense / scipy references, convergence orders; tests/test_oracle_pins.py).
  *

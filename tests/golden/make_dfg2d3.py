@@ -10,10 +10,13 @@ This is the DFG benchmark 2D-3 of Schaefer & Turek, "Benchmark computations of l
 They are the only externally published numbers for what this code path computes (the reference repository ships no
 results), so the stored histories pin the oracle -- assembly, boundary rows, preconditioned solve, time loop and force
 integrals together -- against an independent source; tests/test_oracle_pins.py checks the stored maxima against the
-intervals with a tolerance for the mesh (s = 2: 10 k DoF, s = 4: 41 k DoF) and replays the first steps.
+intervals with a tolerance for the mesh (s = 2: 10 k DoF, s = 4: 41 k DoF, s = 6: 91 k DoF) and replays the first steps.
+Stored results: c_D,max 2.848 / 2.932 / 2.943 at t = 3.93 / 3.94 / 3.94; c_L,max 0.198 / 0.365 / 0.372;
+Delta P(8 s) -0.109 / -0.096 / -0.096.
 
     python tests/golden/make_dfg2d3.py 2        # ~2 minutes on 8 cores
     python tests/golden/make_dfg2d3.py 4        # ~20 minutes
+    python tests/golden/make_dfg2d3.py 6        # ~35 minutes
 """
 import os
 import sys

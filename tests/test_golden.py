@@ -70,11 +70,13 @@ def _dfg(s):
     return np.load(path)
 
 
-@pytest.mark.parametrize("s,tol", [(2, 0.05), (4, 0.02)])
+@pytest.mark.parametrize("s,tol", [(2, 0.05), (4, 0.02), (6, 0.01)])
 def test_dfg_2d3_drag_maximum_against_the_published_interval(s, tol):
     """c_D,max of the stored oracle history lies in the published interval [2.93, 2.97] widened by the mesh
-    tolerance (10 k DoF: 5 %, 41 k DoF: 2 %; P2-P1 converges from below) and is reached at the published time
-    t = 3.93 +- 0.03; lift stays bounded by the published maximum (the coarse meshes damp the vortex shedding)."""
+    tolerance (10 k DoF: 5 %, 41 k DoF: 2 %, 91 k DoF: 1 %; P2-P1 converges from below: 2.848, 2.932, 2.943) and is
+    reached at the published time t = 3.93 +- 0.03.  Lift and Delta P(8 s) are only bounded: they converge with the
+    mesh to c_L,max = 0.37 and Delta P = -0.096 against the published 0.47-0.49 and -0.115..-0.105, which are
+    time-converged values -- the reference's first-order semi-implicit scheme at dt = 0.01 damps the vortex shedding."""
     g = _dfg(s)
     h = g["history"]
     assert h.shape[0] == 800 and abs(h[-1, 0] - 8.0) < 1e-9
@@ -83,8 +85,8 @@ def test_dfg_2d3_drag_maximum_against_the_published_interval(s, tol):
     assert abs(t_cd - DFG_T_CD_MAX) <= 0.03, t_cd
     assert 0.0 < h[:, 3].max() <= DFG_CL_MAX[1] * 1.05
     dp = float(g["pressure_difference"][0])
-    if np.isfinite(dp):  # Delta P(8 s) between the front and the back of the cylinder: depends on the phase of the
-        # vortex shedding, which these meshes under-resolve (c_L,max 0.20 / 0.36 against 0.48) -> 15 % margin
+    if np.isfinite(dp):  # Delta P(8 s) between the front and the back of the cylinder: depends on the phase and
+        # amplitude of the vortex shedding (c_L,max 0.20 / 0.36 / 0.37 against 0.48, see above) -> 15 % margin
         assert DFG_DP[0] * 1.15 <= dp <= DFG_DP[1] * 0.85, dp
 
 
