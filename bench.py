@@ -363,9 +363,19 @@ def run_gpu(args):
     e.stat("t_step_dev_ms_reset")
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    planned, slowest = steps, 0.0
+    for i in range(planned):
+        ts = time.perf_counter()
         its.append(run.step())
         t_prec.append(e.stat("t_prec_ms") * 1e-3); t_solve.append(e.stat("t_solve_ms") * 1e-3)
+        # a step can cost twice the warm-up estimate (230-700 outer iterations): stop early rather than overrun the
+        # budget (every rank takes the same decision; step_host has already synchronised, so this adds no device wait)
+        slowest = max(slowest, time.perf_counter() - ts)
+        over = float((time.perf_counter() - _T0) + extras_s + slowest > budget)
+        if i + 1 < planned and reduce(over) > 0.0:
+            steps = i + 1
+            log(f"budget {budget:.0f} s: stopping after {steps} of {planned} planned steps (slowest step {slowest:.1f} s)")
+            break
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = e.stat("t_step_dev_ms_reset")
