@@ -47,51 +47,72 @@ void Mesh::fix_orientation()
 }
 
 // Faces with exactly one adjacent cell; ids from the classifier.
+// The (dim+1) * n_cells faces are bucketed by their smallest vertex (counting sort, linear) and every bucket --
+// a few dozen faces -- is searched for faces that occur once; the buckets are independent, so the search runs
+// on all host threads (a comparison sort of 18.7 M face records took 10 of the 14 s this mesh generator needed
+// at 4.7 M tetrahedra).  Output order as before: by cell, then by local face.
 void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &classify, bool split_locked)
 {
   const int nv1 = dim + 1;
   const int64_t nc = n_cells();
-  struct FaceRec { int v[3]; int cell; int lf; };
-  std::vector<FaceRec> faces;
-  faces.reserve(size_t(nc) * nv1);
-  for (int64_t c = 0; c < nc; ++c)
-    for (int f = 0; f < nv1; ++f) {
-      FaceRec r; r.v[2] = -1; r.cell = int(c); r.lf = f;
-      int n = 0;
-      for (int k = 0; k < nv1; ++k) if (k != f) r.v[n++] = cells[c * nv1 + k];
-      if (r.v[0] > r.v[1]) std::swap(r.v[0], r.v[1]); // sort the dim (2 | 3) face vertices
-      if (dim == 3) {
-        if (r.v[1] > r.v[2]) std::swap(r.v[1], r.v[2]);
-        if (r.v[0] > r.v[1]) std::swap(r.v[0], r.v[1]);
-      }
-      faces.push_back(r);
+  const int64_t nf = nc * nv1;
+  const size_t nv = verts.size() / dim;
+  // sorted vertices of face f of cell c (v[2] = -1 in 2D)
+  auto face = [&](int64_t id, int v[3]) {
+    const int64_t c = id / nv1;
+    const int f = int(id - c * nv1);
+    int n = 0;
+    v[2] = -1;
+    for (int k = 0; k < nv1; ++k) if (k != f) v[n++] = cells[c * nv1 + k];
+    if (v[0] > v[1]) std::swap(v[0], v[1]);
+    if (dim == 3) {
+      if (v[1] > v[2]) std::swap(v[1], v[2]);
+      if (v[0] > v[1]) std::swap(v[0], v[1]);
     }
-  std::vector<size_t> order(faces.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-    const FaceRec &x = faces[a], &y = faces[b];
-    if (x.v[0] != y.v[0]) return x.v[0] < y.v[0];
-    if (x.v[1] != y.v[1]) return x.v[1] < y.v[1];
-    if (x.v[2] != y.v[2]) return x.v[2] < y.v[2];
-    return a < b;
-  });
-  std::vector<size_t> single;
-  for (size_t i = 0; i < order.size();) {
-    size_t j = i + 1;
-    const FaceRec &x = faces[order[i]];
-    while (j < order.size() && faces[order[j]].v[0] == x.v[0] && faces[order[j]].v[1] == x.v[1] &&
-           faces[order[j]].v[2] == x.v[2]) ++j;
-    if (j - i == 1) single.push_back(order[i]);
-    i = j;
+  };
+  std::vector<int64_t> start(nv + 1, 0);
+  for (int64_t id = 0; id < nf; ++id) {
+    int v[3];
+    face(id, v);
+    start[size_t(v[0]) + 1]++;
   }
-  std::sort(single.begin(), single.end()); // cell order, then local face
+  for (size_t i = 0; i < nv; ++i) start[i + 1] += start[i];
+  struct Rec { int v1, v2; int64_t id; };
+  std::vector<Rec> recs(nf);
+  {
+    std::vector<int64_t> pos(start.begin(), start.end() - 1);
+    for (int64_t id = 0; id < nf; ++id) { // face ids ascend inside every bucket
+      int v[3];
+      face(id, v);
+      recs[pos[v[0]]++] = Rec{v[1], v[2], id};
+    }
+  }
+  std::vector<unsigned char> is_single(nf, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t i = 0; i < int64_t(nv); ++i) {
+    Rec *r = &recs[start[i]];
+    const int64_t n = start[i + 1] - start[i];
+    std::sort(r, r + n, [](const Rec &x, const Rec &y) {
+      if (x.v1 != y.v1) return x.v1 < y.v1;
+      if (x.v2 != y.v2) return x.v2 < y.v2;
+      return x.id < y.id;
+    });
+    for (int64_t a = 0; a < n;) {
+      int64_t b = a + 1;
+      while (b < n && r[b].v1 == r[a].v1 && r[b].v2 == r[a].v2) ++b;
+      if (b - a == 1) is_single[r[a].id] = 1;
+      a = b;
+    }
+  }
   bfaces.clear(); bids.clear(); bcell.clear(); blocal.clear();
-  for (size_t s : single) {
-    const FaceRec &r = faces[s];
-    for (int k = 0; k < dim; ++k) bfaces.push_back(r.v[k]);
-    bids.push_back(classify(*this, r.v));
-    bcell.push_back(r.cell);
-    blocal.push_back(r.lf);
+  for (int64_t id = 0; id < nf; ++id) { // cell order, then local face
+    if (!is_single[id]) continue;
+    int v[3];
+    face(id, v);
+    for (int k = 0; k < dim; ++k) bfaces.push_back(v[k]);
+    bids.push_back(classify(*this, v));
+    bcell.push_back(int(id / nv1));
+    blocal.push_back(int(id % nv1));
   }
   if (split_locked && split_boundary_locked_cells() > 0) build_boundary(classify, false);
 }
