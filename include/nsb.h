@@ -249,6 +249,15 @@ int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, 
                        const int32_t *leaf_levels, int32_t min_active, int32_t bs, double *rel_err, int32_t *stats,
                        int32_t *order_out);
 
+/* CPU-only fingerprint of the HOST side of nsb_set_mesh + nsb_finalize_setup (sparsity patterns, scatter map, SpMV
+ * formats, ILU orderings and their packed storage): the same code runs on a handle without device state and every
+ * array setup would upload is hashed (FNV-1a, upload order) into hashes[cap]; *n_hashes = number of uploads.  Pins the
+ * device data structures on a machine without a GPU (tests/test_setup_fingerprint.py).  Test infrastructure: it
+ * computes nothing else, and the product entry points still fail without a device. */
+int nsb_debug_setup_fingerprint(int32_t dim, int32_t n_cells, const double *vertex_coords, const int32_t *cell_dofs,
+                                int32_t n_u, int32_t n_p, int32_t n_u_owned, int32_t n_p_owned, int32_t ilu_ordering,
+                                int32_t ilu_ordering_schur, uint64_t *hashes, int32_t cap, int32_t *n_hashes);
+
 /* ---- host prerequisites (cold path; replaces deal.II GridIn / DoFHandler in setup()) ---- */
 typedef struct nsh_mesh_s *nsh_mesh;
 typedef struct nsh_dofs_s *nsh_dofs;

@@ -673,14 +673,14 @@ static void sd_set_smem_attr(int bs)
 {
   const int lim = 227 * 1024;
   if (bs == 3) {
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   } else if (bs == 2) {
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   } else {
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NSB_CUDA(cudaFuncSetAttribute(k_sd_trsv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NSB_CUDA_SETUP(cudaFuncSetAttribute(k_sd_trsv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   }
 }
 

@@ -770,7 +770,7 @@ void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<
   if (need > size_t(227) * 1024) throw StateError("bsell: a block does not fit shared memory");
   if (need > size_t(48) * 1024) {
     const int lim = int(need);
-    auto raise = [&](auto kernel) { NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); };
+    auto raise = [&](auto kernel) { NSB_CUDA_SETUP(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); };
     if (ilu.bs_rhs == 3) { raise(k_bsell<3, 0, false, false>); raise(k_bsell<3, 1, false, false>); raise(k_bsell<3, 0, false, true>); raise(k_bsell<3, 1, false, true>); }
     else if (ilu.bs_rhs == 2) { raise(k_bsell<2, 0, false, false>); raise(k_bsell<2, 1, false, false>); raise(k_bsell<2, 0, false, true>); raise(k_bsell<2, 1, false, true>); }
     else { raise(k_bsell<1, 0, true, false>); raise(k_bsell<1, 1, true, false>); raise(k_bsell<1, 0, true, true>); raise(k_bsell<1, 1, true, true>); }

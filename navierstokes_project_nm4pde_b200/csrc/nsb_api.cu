@@ -172,48 +172,53 @@ extern "C" int nsb_set_params(nsb_handle h, const nsb_params *p)
   });
 }
 
+// host side of nsb_set_mesh (no device work: also run by nsb_debug_setup_fingerprint)
+static void set_mesh_host(Handle &H, int32_t n_cells, const double *vertex_coords, const int32_t *cell_dofs, int32_t n_u,
+                          int32_t n_p, int32_t n_u_owned, int32_t n_p_owned)
+{
+  const int dim = H.dim, n2 = H.n2, nv1 = H.nv1, dpc = H.dpc;
+  if (n_cells <= 0 || !vertex_coords || !cell_dofs) throw ArgError("nsb_set_mesh: empty mesh");
+  if (n_u % dim || n_u_owned % dim || n_u_owned > n_u || n_p_owned > n_p || n_u <= 0 || n_p <= 0)
+    throw ArgError("nsb_set_mesh: inconsistent DoF counts");
+  H.nc = n_cells;
+  H.n_nodes = n_u / dim; H.n_p = n_p; H.n_nodes_owned = n_u_owned / dim; H.n_p_owned = n_p_owned;
+  H.h_vcoords.assign(vertex_coords, vertex_coords + size_t(n_cells) * nv1 * dim);
+  H.h_cell_nodes.resize(size_t(n_cells) * n2);
+  H.h_cell_p.resize(size_t(n_cells) * nv1);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    const int32_t *cd = cell_dofs + c * dpc;
+    for (int a = 0; a < n2; ++a) {
+      const int base = (a < nv1) ? a * (dim + 1) : nv1 * (dim + 1) + (a - nv1) * dim;
+      const int d0 = cd[base];
+      if (d0 < 0 || d0 >= n_u || d0 % dim) throw ArgError("nsb_set_mesh: velocity DoFs must be node-interleaved (dof = dim*node + c)");
+      for (int k = 1; k < dim; ++k)
+        if (cd[base + k] != d0 + k) throw ArgError("nsb_set_mesh: velocity DoFs must be node-interleaved (dof = dim*node + c)");
+      H.h_cell_nodes[c * n2 + a] = d0 / dim;
+    }
+    for (int v = 0; v < nv1; ++v) {
+      const int p = cd[v * (dim + 1) + dim] - n_u;
+      if (p < 0 || p >= n_p) throw ArgError("nsb_set_mesh: pressure DoF out of range");
+      H.h_cell_p[c * nv1 + v] = p;
+    }
+    // orientation / degeneracy check
+    const double *x = &H.h_vcoords[c * nv1 * dim];
+    double J[3][3];
+    for (int r = 0; r < dim; ++r)
+      for (int k = 0; k < dim; ++k) J[r][k] = x[(k + 1) * dim + r] - x[r];
+    const double det = dim == 2 ? J[0][0] * J[1][1] - J[0][1] * J[1][0]
+                                : J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                                      J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                      J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    if (!(det > 0)) throw ArgError("nsb_set_mesh: cell with non-positive Jacobian");
+  }
+  H.have_mesh = true;
+  H.finalized = H.assembled = H.prec_ready = false;
+}
+
 extern "C" int nsb_set_mesh(nsb_handle h, int32_t n_cells, const double *vertex_coords, const int32_t *cell_dofs,
                             int32_t n_u, int32_t n_p, int32_t n_u_owned, int32_t n_p_owned)
 {
-  return guarded(h, [&](Handle &H) {
-    const int dim = H.dim, n2 = H.n2, nv1 = H.nv1, dpc = H.dpc;
-    if (n_cells <= 0 || !vertex_coords || !cell_dofs) throw ArgError("nsb_set_mesh: empty mesh");
-    if (n_u % dim || n_u_owned % dim || n_u_owned > n_u || n_p_owned > n_p || n_u <= 0 || n_p <= 0)
-      throw ArgError("nsb_set_mesh: inconsistent DoF counts");
-    H.nc = n_cells;
-    H.n_nodes = n_u / dim; H.n_p = n_p; H.n_nodes_owned = n_u_owned / dim; H.n_p_owned = n_p_owned;
-    H.h_vcoords.assign(vertex_coords, vertex_coords + size_t(n_cells) * nv1 * dim);
-    H.h_cell_nodes.resize(size_t(n_cells) * n2);
-    H.h_cell_p.resize(size_t(n_cells) * nv1);
-    for (int64_t c = 0; c < n_cells; ++c) {
-      const int32_t *cd = cell_dofs + c * dpc;
-      for (int a = 0; a < n2; ++a) {
-        const int base = (a < nv1) ? a * (dim + 1) : nv1 * (dim + 1) + (a - nv1) * dim;
-        const int d0 = cd[base];
-        if (d0 < 0 || d0 >= n_u || d0 % dim) throw ArgError("nsb_set_mesh: velocity DoFs must be node-interleaved (dof = dim*node + c)");
-        for (int k = 1; k < dim; ++k)
-          if (cd[base + k] != d0 + k) throw ArgError("nsb_set_mesh: velocity DoFs must be node-interleaved (dof = dim*node + c)");
-        H.h_cell_nodes[c * n2 + a] = d0 / dim;
-      }
-      for (int v = 0; v < nv1; ++v) {
-        const int p = cd[v * (dim + 1) + dim] - n_u;
-        if (p < 0 || p >= n_p) throw ArgError("nsb_set_mesh: pressure DoF out of range");
-        H.h_cell_p[c * nv1 + v] = p;
-      }
-      // orientation / degeneracy check
-      const double *x = &H.h_vcoords[c * nv1 * dim];
-      double J[3][3];
-      for (int r = 0; r < dim; ++r)
-        for (int k = 0; k < dim; ++k) J[r][k] = x[(k + 1) * dim + r] - x[r];
-      const double det = dim == 2 ? J[0][0] * J[1][1] - J[0][1] * J[1][0]
-                                  : J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
-                                        J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-                                        J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-      if (!(det > 0)) throw ArgError("nsb_set_mesh: cell with non-positive Jacobian");
-    }
-    H.have_mesh = true;
-    H.finalized = H.assembled = H.prec_ready = false;
-  });
+  return guarded(h, [&](Handle &H) { set_mesh_host(H, n_cells, vertex_coords, cell_dofs, n_u, n_p, n_u_owned, n_p_owned); });
 }
 
 static void tabulate(Handle &H, int nq, const double *xi, const double *w)
@@ -269,110 +274,115 @@ static std::vector<T> interleave32(const std::vector<T> &in, int64_t nc, int64_t
   return out;
 }
 
+// nsb_finalize_setup: everything static is built on the host here and uploaded (the dry run of
+// nsb_debug_setup_fingerprint hashes the uploads instead)
+static void finalize_setup(Handle &H)
+{
+  if (!H.have_mesh || !H.have_quad) throw StateError("nsb_finalize_setup: mesh and quadrature must be set first");
+  const int dim = H.dim, n2 = H.n2, nv1 = H.nv1;
+  const int64_t nc = H.nc;
+  H.nc_pad = (nc + 31) / 32 * 32;
+  // NSB_VERBOSE=1: where the (host-side, cold-path) setup time goes
+  const bool verbose = getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 0;
+  auto t_last = std::chrono::steady_clock::now();
+  auto phase = [&](const char *what) {
+    if (!verbose) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[nsb setup rank %d] %-28s %8.2f s\n", H.rank, what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
+  // patterns (DoFTools::make_sparsity_pattern with the coupling table of NavierStokes2D.cpp:109-119)
+  build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_nodes.data(), n2, H.n_nodes, H.n_nodes_owned, H.n_nodes, H.hFs);
+  build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_p.data(), nv1, H.n_nodes, H.n_nodes, H.n_p, H.hBt);
+  build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_nodes.data(), n2, H.n_p, H.n_p_owned, H.n_nodes, H.hB);
+  build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_p.data(), nv1, H.n_p, H.n_p_owned, H.n_p, H.hMp);
+  phase("sparsity patterns");
+  symbolic_product(H.hB, H.hBt, H.hS);
+  phase("symbolic Schur product");
+  H.Fs.upload_pattern(H.hFs, 1);
+  H.Bt.upload_pattern(H.hBt, dim);
+  H.B.upload_pattern(H.hB, dim);
+  H.Mp.upload_pattern(H.hMp, 1);
+  H.S.upload_pattern(H.hS, 1);
+  H.d_K.alloc(H.Fs.nnz); H.d_M.alloc(H.Fs.nnz); H.d_A.alloc(H.Fs.nnz); H.d_C.alloc(H.Fs.nnz);
+  H.d_K.zero(); H.d_M.zero(); H.d_A.zero(); H.d_C.zero();
+  // diagonal positions and the scatter map of the step kernel
+  std::vector<int> diag(H.n_nodes_owned);
+  for (int i = 0; i < H.n_nodes_owned; ++i) diag[i] = find_in_row(H.hFs, i, i);
+  H.d_diagF.upload(diag);
+  {
+    std::vector<int> map(size_t(H.nc_pad) * n2 * n2, -1);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < nc; ++c) {
+      const int *cn = &H.h_cell_nodes[c * n2];
+      for (int i = 0; i < n2; ++i) {
+        if (cn[i] >= H.n_nodes_owned) continue;
+        for (int j = 0; j < n2; ++j)
+          map[((c >> 5) * (n2 * n2) + i * n2 + j) * 32 + (c & 31)] = find_in_row(H.hFs, cn[i], cn[j]);
+      }
+    }
+    H.d_mapF.upload(map);
+  }
+  phase("uploads, scatter map");
+  H.d_vcoords.upload(interleave32<double>(H.h_vcoords, nc, H.nc_pad, nv1 * dim, 0.0));
+  H.d_cell_nodes.upload(interleave32<int>(H.h_cell_nodes, nc, H.nc_pad, n2, -1));
+  H.d_cell_p.upload(interleave32<int>(H.h_cell_p, nc, H.nc_pad, nv1, 0));
+  H.d_step_tensor.alloc(1);
+  {
+    StepTensor t;
+    build_step_tensor(H.h_tab, dim, H.prm.variant != NSB_VARIANT_3D, t);
+    NSB_CUDA_SETUP(cudaMemcpy(H.d_step_tensor.p, &t, sizeof(t), cudaMemcpyHostToDevice));
+  }
+  // vectors
+  const size_t nl = size_t(H.n_local());
+  H.d_sol.alloc(nl); H.d_rhs.alloc(nl);
+  H.d_sol.zero(); H.d_rhs.zero();
+  const size_t nun = size_t(dim) * H.n_nodes;
+  H.d_D.alloc(nun); H.d_Dinv.alloc(nun); H.d_negDinv.alloc(nun);
+  H.d_D.zero(); H.d_Dinv.zero(); H.d_negDinv.zero();
+  H.d_massdiag.alloc(H.n_nodes_owned); H.d_masslump.alloc(H.n_nodes_owned);
+  H.d_neumann.alloc(size_t(H.nu_owned()));
+  H.d_neumann.zero();
+  // ILU(0) schedules (static pattern => symbolic work once)
+  ilu_reset_graphs(H); // schedules are rebuilt: drop graphs captured for the old ones
+  phase("mesh arrays, vectors");
+  stream_build_spmv(H);
+  if (dim == 3) {
+    sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, sell_lanes_for(H.hFs.n_rows), H.sellF);
+    H.d_xpad.alloc(size_t(4) * H.n_nodes);
+    H.d_xpad.zero();
+  }
+  H.sellF_dirty = true;
+  phase("SpMV formats (SELL, stream)");
+  std::vector<double> xyz_n, xyz_p; // support points of the P2 nodes / pressure vertices (subdomain ordering)
+  const int ord_s = H.prm.ilu_ordering_schur < 0 ? H.prm.ilu_ordering : H.prm.ilu_ordering_schur;
+  if (H.prm.ilu_ordering == 3 || ord_s == 3) {
+    xyz_n.assign(size_t(H.n_nodes) * dim, 0.0);
+    xyz_p.assign(size_t(H.n_p) * dim, 0.0);
+    for (int64_t c = 0; c < nc; ++c) {
+      const double *X = &H.h_vcoords[c * nv1 * dim];
+      for (int a = 0; a < n2; ++a) {
+        const int node = H.h_cell_nodes[c * n2 + a];
+        const int va = a < nv1 ? a : kEdgeA[a - nv1], vb = a < nv1 ? a : kEdgeB[a - nv1];
+        for (int d = 0; d < dim; ++d) xyz_n[size_t(node) * dim + d] = 0.5 * (X[va * dim + d] + X[vb * dim + d]);
+      }
+      for (int v = 0; v < nv1; ++v)
+        for (int d = 0; d < dim; ++d) xyz_p[size_t(H.h_cell_p[c * nv1 + v]) * dim + d] = X[v * dim + d];
+    }
+  }
+  ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering, xyz_n.empty() ? nullptr : xyz_n.data(), dim);
+  phase("ILU schedule F");
+  ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, ord_s, xyz_p.empty() ? nullptr : xyz_p.data(), dim);
+  phase("ILU schedule S");
+  solver_alloc(H);
+  NSB_CUDA_SETUP(cudaDeviceSynchronize());
+  H.finalized = true;
+  H.assembled = H.prec_ready = false;
+}
+
 extern "C" int nsb_finalize_setup(nsb_handle h)
 {
-  return guarded(h, [&](Handle &H) {
-    if (!H.have_mesh || !H.have_quad) throw StateError("nsb_finalize_setup: mesh and quadrature must be set first");
-    const int dim = H.dim, n2 = H.n2, nv1 = H.nv1;
-    const int64_t nc = H.nc;
-    H.nc_pad = (nc + 31) / 32 * 32;
-    // NSB_VERBOSE=1: where the (host-side, cold-path) setup time goes
-    const bool verbose = getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 0;
-    auto t_last = std::chrono::steady_clock::now();
-    auto phase = [&](const char *what) {
-      if (!verbose) return;
-      const auto now = std::chrono::steady_clock::now();
-      std::fprintf(stderr, "[nsb setup rank %d] %-28s %8.2f s\n", H.rank, what, std::chrono::duration<double>(now - t_last).count());
-      t_last = now;
-    };
-    // patterns (DoFTools::make_sparsity_pattern with the coupling table of NavierStokes2D.cpp:109-119)
-    build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_nodes.data(), n2, H.n_nodes, H.n_nodes_owned, H.n_nodes, H.hFs);
-    build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_p.data(), nv1, H.n_nodes, H.n_nodes, H.n_p, H.hBt);
-    build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_nodes.data(), n2, H.n_p, H.n_p_owned, H.n_nodes, H.hB);
-    build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_p.data(), nv1, H.n_p, H.n_p_owned, H.n_p, H.hMp);
-    phase("sparsity patterns");
-    symbolic_product(H.hB, H.hBt, H.hS);
-    phase("symbolic Schur product");
-    H.Fs.upload_pattern(H.hFs, 1);
-    H.Bt.upload_pattern(H.hBt, dim);
-    H.B.upload_pattern(H.hB, dim);
-    H.Mp.upload_pattern(H.hMp, 1);
-    H.S.upload_pattern(H.hS, 1);
-    H.d_K.alloc(H.Fs.nnz); H.d_M.alloc(H.Fs.nnz); H.d_A.alloc(H.Fs.nnz); H.d_C.alloc(H.Fs.nnz);
-    H.d_K.zero(); H.d_M.zero(); H.d_A.zero(); H.d_C.zero();
-    // diagonal positions and the scatter map of the step kernel
-    std::vector<int> diag(H.n_nodes_owned);
-    for (int i = 0; i < H.n_nodes_owned; ++i) diag[i] = find_in_row(H.hFs, i, i);
-    H.d_diagF.upload(diag);
-    {
-      std::vector<int> map(size_t(H.nc_pad) * n2 * n2, -1);
-#pragma omp parallel for schedule(static)
-      for (int64_t c = 0; c < nc; ++c) {
-        const int *cn = &H.h_cell_nodes[c * n2];
-        for (int i = 0; i < n2; ++i) {
-          if (cn[i] >= H.n_nodes_owned) continue;
-          for (int j = 0; j < n2; ++j)
-            map[((c >> 5) * (n2 * n2) + i * n2 + j) * 32 + (c & 31)] = find_in_row(H.hFs, cn[i], cn[j]);
-        }
-      }
-      H.d_mapF.upload(map);
-    }
-    phase("uploads, scatter map");
-    H.d_vcoords.upload(interleave32<double>(H.h_vcoords, nc, H.nc_pad, nv1 * dim, 0.0));
-    H.d_cell_nodes.upload(interleave32<int>(H.h_cell_nodes, nc, H.nc_pad, n2, -1));
-    H.d_cell_p.upload(interleave32<int>(H.h_cell_p, nc, H.nc_pad, nv1, 0));
-    H.d_step_tensor.alloc(1);
-    {
-      StepTensor t;
-      build_step_tensor(H.h_tab, dim, H.prm.variant != NSB_VARIANT_3D, t);
-      NSB_CUDA(cudaMemcpy(H.d_step_tensor.p, &t, sizeof(t), cudaMemcpyHostToDevice));
-    }
-    // vectors
-    const size_t nl = size_t(H.n_local());
-    H.d_sol.alloc(nl); H.d_rhs.alloc(nl);
-    H.d_sol.zero(); H.d_rhs.zero();
-    const size_t nun = size_t(dim) * H.n_nodes;
-    H.d_D.alloc(nun); H.d_Dinv.alloc(nun); H.d_negDinv.alloc(nun);
-    H.d_D.zero(); H.d_Dinv.zero(); H.d_negDinv.zero();
-    H.d_massdiag.alloc(H.n_nodes_owned); H.d_masslump.alloc(H.n_nodes_owned);
-    H.d_neumann.alloc(size_t(H.nu_owned()));
-    H.d_neumann.zero();
-    // ILU(0) schedules (static pattern => symbolic work once)
-    ilu_reset_graphs(H); // schedules are rebuilt: drop graphs captured for the old ones
-    phase("mesh arrays, vectors");
-    stream_build_spmv(H);
-    if (dim == 3) {
-      sell_build(H.hFs.rowptr, H.hFs.colind, {}, {0, H.hFs.n_rows}, 2048, sell_lanes_for(H.hFs.n_rows), H.sellF);
-      H.d_xpad.alloc(size_t(4) * H.n_nodes);
-      H.d_xpad.zero();
-    }
-    H.sellF_dirty = true;
-    phase("SpMV formats (SELL, stream)");
-    std::vector<double> xyz_n, xyz_p; // support points of the P2 nodes / pressure vertices (subdomain ordering)
-    const int ord_s = H.prm.ilu_ordering_schur < 0 ? H.prm.ilu_ordering : H.prm.ilu_ordering_schur;
-    if (H.prm.ilu_ordering == 3 || ord_s == 3) {
-      xyz_n.assign(size_t(H.n_nodes) * dim, 0.0);
-      xyz_p.assign(size_t(H.n_p) * dim, 0.0);
-      for (int64_t c = 0; c < nc; ++c) {
-        const double *X = &H.h_vcoords[c * nv1 * dim];
-        for (int a = 0; a < n2; ++a) {
-          const int node = H.h_cell_nodes[c * n2 + a];
-          const int va = a < nv1 ? a : kEdgeA[a - nv1], vb = a < nv1 ? a : kEdgeB[a - nv1];
-          for (int d = 0; d < dim; ++d) xyz_n[size_t(node) * dim + d] = 0.5 * (X[va * dim + d] + X[vb * dim + d]);
-        }
-        for (int v = 0; v < nv1; ++v)
-          for (int d = 0; d < dim; ++d) xyz_p[size_t(H.h_cell_p[c * nv1 + v]) * dim + d] = X[v * dim + d];
-      }
-    }
-    ilu_build(H, H.iluF, H.hFs, H.n_nodes_owned, dim, H.prm.ilu_ordering, xyz_n.empty() ? nullptr : xyz_n.data(), dim);
-    phase("ILU schedule F");
-    ilu_build(H, H.iluS, H.hS, H.n_p_owned, 1, ord_s, xyz_p.empty() ? nullptr : xyz_p.data(), dim);
-    phase("ILU schedule S");
-    solver_alloc(H);
-    NSB_CUDA(cudaDeviceSynchronize());
-    H.finalized = true;
-    H.assembled = H.prec_ready = false;
-  });
+  return guarded(h, [&](Handle &H) { finalize_setup(H); });
 }
 
 // ---- reference-layout views ------------------------------------------------------------------
@@ -545,6 +555,44 @@ extern "C" int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_
   } catch (const std::exception &) {
     return NSB_ERR_STATE;
   }
+}
+
+// ---- CPU-only fingerprint of the host side of setup (no GPU needed; tests/test_setup_fingerprint.py) ------
+// Runs set_mesh_host + finalize_setup on a handle that owns no device state, with the setup dry run on: every array
+// setup would upload is hashed in upload order.  Test infrastructure; computes nothing and is not reachable from the
+// product entry points.
+extern "C" int nsb_debug_setup_fingerprint(int32_t dim, int32_t n_cells, const double *vertex_coords, const int32_t *cell_dofs,
+                                           int32_t n_u, int32_t n_p, int32_t n_u_owned, int32_t n_p_owned,
+                                           int32_t ilu_ordering, int32_t ilu_ordering_schur, uint64_t *hashes, int32_t cap,
+                                           int32_t *n_hashes)
+{
+  if ((dim != 2 && dim != 3) || !n_hashes || (cap > 0 && !hashes) || ilu_ordering < 0 || ilu_ordering > 3 ||
+      ilu_ordering_schur < -1 || ilu_ordering_schur > 3)
+    return NSB_ERR_ARG;
+  if (g_dry.on) return NSB_ERR_STATE; // one dry run at a time (the log is process-wide)
+  int rc = NSB_OK;
+  nsb_handle_s *h = nullptr;
+  try {
+    h = new nsb_handle_s();
+    Handle &H = h->H;
+    H.dim = dim; H.n2 = n2_of(dim); H.nv1 = dim + 1; H.dpc = dpc_of(dim);
+    nsb_default_params(&H.prm, dim == 2 ? NSB_VARIANT_2D : NSB_VARIANT_3D);
+    H.prm.ilu_ordering = ilu_ordering;
+    H.prm.ilu_ordering_schur = ilu_ordering_schur;
+    g_dry.log.clear();
+    g_dry.on = true;
+    set_mesh_host(H, n_cells, vertex_coords, cell_dofs, n_u, n_p, n_u_owned, n_p_owned);
+    std::memset(&H.h_tab, 0, sizeof(H.h_tab)); // the quadrature tables do not enter any static structure
+    H.have_quad = true;
+    finalize_setup(H);
+  } catch (const ArgError &) { rc = NSB_ERR_ARG;
+  } catch (const std::exception &) { rc = NSB_ERR_STATE; }
+  delete h; // buffers were never allocated: nothing to free on a device
+  g_dry.on = false;
+  *n_hashes = int32_t(g_dry.log.size());
+  for (int32_t k = 0; k < cap && k < *n_hashes; ++k) hashes[k] = g_dry.log[k];
+  g_dry.log.clear();
+  return rc;
 }
 
 // ---- drag / lift on the device (kernels_post.cu) ---------------------------------------------

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -78,6 +79,33 @@ struct StepTensor {
   double Mh[10][10];
 };
 
+// Setup dry run -- TEST INFRASTRUCTURE (nsb_debug_setup_fingerprint, tests/test_setup_fingerprint.py): while it is on,
+// the device buffers of setup are not allocated and every array setup would upload is hashed (FNV-1a over its bytes)
+// into `log` instead, so the host-built device data structures (patterns, scatter map, SELL / block-SELL storage, ILU
+// orderings) can be pinned on a machine without a GPU.  Nothing is computed in this mode and no entry point of the
+// product path ever switches it on: without a device nsb_create still fails ("no CPU fallback").
+struct SetupDryRun {
+  bool on = false;
+  std::vector<uint64_t> log;
+  void record(uint64_t tag, const void *data, size_t bytes)
+  {
+    uint64_t h = 1469598103934665603ull ^ tag;
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    // eight bytes at a time (the arrays are hundreds of MB at bench size), tail byte by byte
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+      uint64_t w;
+      std::memcpy(&w, b + i, 8);
+      h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    log.push_back(h ^ (uint64_t(bytes) << 1));
+  }
+};
+inline SetupDryRun g_dry;
+// raw CUDA calls that setup makes besides DevBuf (attributes, small copies, synchronisation): skipped in a dry run
+#define NSB_CUDA_SETUP(call) do { if (!nsb::g_dry.on) NSB_CUDA(call); } while (0)
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -86,15 +114,18 @@ struct DevBuf {
   {
     release();
     n = count;
+    if (g_dry.on) { g_dry.record(0xA110C, &count, sizeof(count)); return; }
     if (count) NSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
   }
   void upload(const std::vector<T> &h)
   {
+    if (g_dry.on) { n = h.size(); g_dry.record(sizeof(T), h.data(), h.size() * sizeof(T)); return; }
     if (n != h.size()) alloc(h.size());
     if (n) NSB_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
   }
   void zero(cudaStream_t s = 0)
   {
+    if (g_dry.on) return;
     if (n) NSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
   }
   void release()
