@@ -8,6 +8,7 @@
 // Layout: the velocity block is stored once as the scalar node graph F_s and applied to the
 // `dim` interleaved components of each P2 node; B / Bt keep `dim` values per (vertex,node) pair.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -930,31 +931,53 @@ static void permute_pattern(const Csr &A, const std::vector<int> &order, int n_o
                             std::vector<int> &colind, std::vector<int> &src, std::vector<int> &diagpos)
 {
   const int n = A.n_rows;
+  const int lim = std::min(n_owned_cols, n); // Ifpack_LocalFilter: off-process columns are dropped
   std::vector<int> pos(n_owned_cols > n ? n_owned_cols : n, -1);
+#pragma omp parallel for schedule(static)
   for (int k = 0; k < n; ++k) pos[order[k]] = k;
   rowptr.assign(n + 1, 0);
   diagpos.assign(n, 0);
-  colind.clear(); src.clear();
-  colind.reserve(A.colind.size());
-  src.reserve(A.colind.size());
-  std::vector<std::pair<int, int>> row;
+  // rows are independent: count, prefix sum, then fill and sort every row on its own (all host threads)
+  int missing_diag = 0;
+#pragma omp parallel for schedule(static) reduction(+ : missing_diag)
   for (int k = 0; k < n; ++k) {
     const int i = order[k];
-    row.clear();
+    int cnt = 0;
     bool have_diag = false;
     for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
       const int j = A.colind[e];
-      if (j >= n_owned_cols || j >= n) continue; // Ifpack_LocalFilter: off-process columns are dropped
+      if (j >= lim) continue;
       if (j == i) have_diag = true;
-      row.emplace_back(pos[j], e);
+      ++cnt;
     }
-    if (!have_diag) throw StateError("ILU: structurally missing diagonal");
-    std::sort(row.begin(), row.end());
-    for (auto &pe : row) { colind.push_back(pe.first); src.push_back(pe.second); }
-    rowptr[k + 1] = int(colind.size());
-    int dp = rowptr[k];
-    while (colind[dp] != k) ++dp;
-    diagpos[k] = dp;
+    if (!have_diag) ++missing_diag;
+    rowptr[k + 1] = cnt;
+  }
+  if (missing_diag) throw StateError("ILU: structurally missing diagonal");
+  for (int k = 0; k < n; ++k) rowptr[k + 1] += rowptr[k];
+  colind.assign(size_t(rowptr[n]), 0);
+  src.assign(size_t(rowptr[n]), 0);
+#pragma omp parallel
+  {
+    std::vector<std::pair<int, int>> row;
+#pragma omp for schedule(static)
+    for (int k = 0; k < n; ++k) {
+      const int i = order[k];
+      row.clear();
+      for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+        const int j = A.colind[e];
+        if (j >= lim) continue;
+        row.emplace_back(pos[j], e);
+      }
+      std::sort(row.begin(), row.end());
+      int o = rowptr[k];
+      for (auto &pe : row) {
+        if (pe.first == k) diagpos[k] = o;
+        colind[o] = pe.first;
+        src[o] = pe.second;
+        ++o;
+      }
+    }
   }
 }
 
@@ -1014,6 +1037,14 @@ static int sd_min_active()
 void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rhs, int ordering, const double *xyz, int gdim)
 {
   const int n = A.n_rows;
+  const bool verbose = getenv("NSB_VERBOSE") && atoi(getenv("NSB_VERBOSE")) > 1;
+  auto t_last = std::chrono::steady_clock::now();
+  auto phase = [&](const char *what) {
+    if (!verbose) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[nsb ilu_build] %-24s %8.2f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   ilu.n = n;
   ilu.bs_rhs = bs_rhs;
   ilu.h_order.clear();
@@ -1035,8 +1066,10 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
   }
   else { ilu.h_order.resize(n); for (int i = 0; i < n; ++i) ilu.h_order[i] = i; }
   const std::vector<int> &order = ilu.h_order;
+  phase("ordering");
   std::vector<int> rowptr, colind, src, diagpos;
   permute_pattern(A, order, n_owned_cols, rowptr, colind, src, diagpos);
+  phase("permuted pattern");
   ilu.nnz = int64_t(colind.size());
   ilu.rowptr.upload(rowptr);
   ilu.colind.upload(colind);
@@ -1065,9 +1098,11 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
     // per block colour (bsell_trsv)
     level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);
     ilu.lvl_rows_f.upload(rows);
+    phase("level schedule");
     ilu.lvl_ptr_b.assign(1, 0);
     ilu.colour_ptr = colour_ptr;
     bsell_build(ilu, rowptr, colind, diagpos, blk_ptr, colour_blk);
+    phase("block-SELL storage");
     ilu.bsell = true;
     return;
   }
@@ -1087,7 +1122,9 @@ void ilu_build(Handle &H, DevIlu &ilu, const Csr &A, int n_owned_cols, int bs_rh
       ilu.lvl_ptr_b[nc - c] = int(rb.size());
     }
     ilu.lvl_rows_b.upload(rb);
+    phase("colour schedule");
     stream_build_ilu(H, ilu, rowptr, colind, diagpos, colour_ptr);
+    phase("L / U streams, SELL");
     return;
   }
   level_schedule(n, rowptr, colind, true, ilu.lvl_ptr_f, rows);

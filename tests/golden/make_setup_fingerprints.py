@@ -8,13 +8,15 @@ import sys
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
-from test_setup_fingerprint import CASES, ORDERINGS, fingerprint  # noqa: E402
+from test_setup_fingerprint import CASES, ORDERINGS, fingerprint, owned_prefix  # noqa: E402
 
 out = {}
 for name, make in CASES.items():
     mesh = make()
     for o1, o2 in ORDERINGS:
         out[f"{name}/{o1}/{o2}"] = fingerprint(mesh, o1, o2)
+        if o1 != 3:
+            out[f"{name}/{o1}/{o2}/ghosts"] = fingerprint(mesh, o1, o2, owned_prefix(mesh))
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "setup_fingerprints.json"), "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
 print(len(out), "fingerprints written")
