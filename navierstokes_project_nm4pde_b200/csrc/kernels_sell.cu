@@ -160,48 +160,71 @@ __global__ void k_pad3(int n_nodes, int n_owned, int goff, const double *__restr
 void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
                 const std::vector<int> &ranges, int window, int lanes, DevSell &out)
 {
-  std::vector<int> slice_ptr(1, 0), rowid, col, map;
   out.range_slice.assign(ranges.size(), 0);
   out.lanes = lanes;
   const int R = 32 / lanes; // rows per slice
-  std::vector<int> rows;
+  // 1. rows of every range, length-sorted inside windows (the windows are independent: all host threads)
+  size_t n_rows = 0;
+  for (size_t g = 0; g + 1 < ranges.size(); ++g) n_rows += size_t(ranges[g + 1] - ranges[g]);
+  std::vector<int> rows(n_rows);
+  struct Slice { size_t first; int ns; }; // position of the slice's first row in `rows`, rows in the slice
+  std::vector<Slice> slices;
+  std::vector<std::pair<size_t, size_t>> windows;
+  size_t base_r = 0;
   for (size_t g = 0; g + 1 < ranges.size(); ++g) {
-    out.range_slice[g] = int(slice_ptr.size()) - 1;
+    out.range_slice[g] = int(slices.size());
     const int a = ranges[g], b = ranges[g + 1];
-    rows.resize(b - a);
-    std::iota(rows.begin(), rows.end(), a);
-    for (int w0 = 0; w0 < b - a; w0 += window) {
-      const int w1 = std::min(b - a, w0 + window);
-      std::stable_sort(rows.begin() + w0, rows.begin() + w1, [&](int x, int y) {
-        return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
-      });
+    std::iota(rows.begin() + base_r, rows.begin() + base_r + (b - a), a);
+    for (int w0 = 0; w0 < b - a; w0 += window) windows.emplace_back(base_r + w0, base_r + std::min(b - a, w0 + window));
+    for (int s = 0; s < b - a; s += R) slices.push_back(Slice{base_r + s, std::min(R, b - a - s)});
+    base_r += size_t(b - a);
+  }
+  const int64_t nw = int64_t(windows.size());
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t w = 0; w < nw; ++w)
+    std::stable_sort(rows.begin() + windows[w].first, rows.begin() + windows[w].second, [&](int x, int y) {
+      return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+    });
+  // 2. slice lengths (groups of 32 slots), prefix sum
+  const int64_t nsl = int64_t(slices.size());
+  std::vector<int> slice_ptr(size_t(nsl) + 1, 0);
+  std::vector<int64_t> off(size_t(nsl) + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nsl; ++i) {
+    int len = 0;
+    for (int l = 0; l < slices[i].ns; ++l) {
+      const int r = rows[slices[i].first + l];
+      len = std::max(len, (rowptr[r + 1] - rowptr[r] + lanes - 1) / lanes);
     }
-    for (int s = 0; s < b - a; s += R) {
-      const int ns = std::min(R, b - a - s);
-      int len = 0; // groups of 32 slots
-      for (int l = 0; l < ns; ++l)
-        len = std::max(len, (rowptr[rows[s + l] + 1] - rowptr[rows[s + l]] + lanes - 1) / lanes);
-      for (int l = 0; l < 32; ++l) rowid.push_back(l / lanes < ns ? rows[s + l / lanes] : -1);
-      const size_t base = col.size();
-      col.resize(base + size_t(len) * 32);
-      map.resize(base + size_t(len) * 32);
-      for (int l = 0; l < 32; ++l) {
-        const int r = l / lanes < ns ? rows[s + l / lanes] : -1, q = l % lanes;
-        const int rl = r >= 0 ? rowptr[r + 1] - rowptr[r] : 0;
-        const int pad_col = (r >= 0 && rl > 0) ? colind[rowptr[r]] : 0;
-        for (int k = 0; k < len; ++k) {
-          const size_t o = base + size_t(k) * 32 + l;
-          const int e = k * lanes + q;
-          if (e < rl) { col[o] = colind[rowptr[r] + e]; map[o] = src.empty() ? rowptr[r] + e : src[rowptr[r] + e]; }
-          else { col[o] = pad_col; map[o] = -1; }
-        }
+    off[i + 1] = int64_t(len) * 32;
+  }
+  for (int64_t i = 0; i < nsl; ++i) off[i + 1] += off[i];
+  if (off[nsl] > int64_t(0x7fffffff)) throw StateError("SELL: more than 2^31 slots");
+  for (int64_t i = 0; i <= nsl; ++i) slice_ptr[i] = int(off[i]);
+  // 3. fill the slices
+  const size_t n_slots = size_t(off[nsl]);
+  std::vector<int> rowid(size_t(nsl) * 32), col(n_slots), map(n_slots);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nsl; ++i) {
+    const int ns = slices[i].ns;
+    const int *rs = &rows[slices[i].first];
+    const size_t base = size_t(off[i]);
+    const int len = int((off[i + 1] - off[i]) / 32);
+    for (int l = 0; l < 32; ++l) {
+      const int r = l / lanes < ns ? rs[l / lanes] : -1, q = l % lanes;
+      rowid[size_t(i) * 32 + l] = r;
+      const int rl = r >= 0 ? rowptr[r + 1] - rowptr[r] : 0;
+      const int pad_col = (r >= 0 && rl > 0) ? colind[rowptr[r]] : 0;
+      for (int k = 0; k < len; ++k) {
+        const size_t o = base + size_t(k) * 32 + l;
+        const int e = k * lanes + q;
+        if (e < rl) { col[o] = colind[rowptr[r] + e]; map[o] = src.empty() ? rowptr[r] + e : src[rowptr[r] + e]; }
+        else { col[o] = pad_col; map[o] = -1; }
       }
-      if (col.size() > size_t(0x7fffffff)) throw StateError("SELL: more than 2^31 slots");
-      slice_ptr.push_back(int(col.size()));
     }
   }
-  out.range_slice.back() = int(slice_ptr.size()) - 1;
-  out.n_slices = int(slice_ptr.size()) - 1;
+  out.range_slice.back() = int(nsl);
+  out.n_slices = int(nsl);
   out.n_slots = int64_t(col.size());
   out.slice_ptr.upload(slice_ptr);
   out.rowid.upload(rowid);

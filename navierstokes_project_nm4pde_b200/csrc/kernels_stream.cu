@@ -235,10 +235,17 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
   const int n = ilu.n;
   std::vector<int> Lp(n + 1, 0), Up(n + 1, 0), Lc, Uc, mapL, mapU;
   for (int k = 0; k < n; ++k) {
-    for (int e = rowptr[k]; e < diagpos[k]; ++e) { Lc.push_back(colind[e]); mapL.push_back(e); }
-    for (int e = diagpos[k] + 1; e < rowptr[k + 1]; ++e) { Uc.push_back(colind[e]); mapU.push_back(e); }
-    Lp[k + 1] = int(Lc.size());
-    Up[k + 1] = int(Uc.size());
+    Lp[k + 1] = Lp[k] + (diagpos[k] - rowptr[k]);
+    Up[k + 1] = Up[k] + (rowptr[k + 1] - diagpos[k] - 1);
+  }
+  Lc.resize(size_t(Lp[n])); mapL.resize(size_t(Lp[n]));
+  Uc.resize(size_t(Up[n])); mapU.resize(size_t(Up[n]));
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < n; ++k) {
+    int o = Lp[k];
+    for (int e = rowptr[k]; e < diagpos[k]; ++e, ++o) { Lc[o] = colind[e]; mapL[o] = e; }
+    o = Up[k];
+    for (int e = diagpos[k] + 1; e < rowptr[k + 1]; ++e, ++o) { Uc[o] = colind[e]; mapU[o] = e; }
   }
   ilu.colour_ptr = colour_ptr;
   const int nc = int(colour_ptr.size()) - 1;
