@@ -668,93 +668,162 @@ __global__ void __launch_bounds__(kBW * 32, 8) k_bsell(int b0, int b1, const int
   }
 }
 
+// The blocks are independent, so runs of kBsellChunk consecutive blocks are packed by different host threads into
+// chunk-local arrays (positions relative to the chunk) and the chunks are concatenated in order afterwards: the result
+// does not depend on the number of threads.
+namespace {
+constexpr int kBsellChunk = 2048;
+struct BsellChunk {
+  std::vector<int> e_ptr, i_ptr, x_ptr;    // [blocks of the chunk + 1], relative to the chunk
+  std::vector<int> e_map, e_gcol, i_map, x_ids;
+  std::vector<unsigned short> e_col;
+  std::vector<unsigned char> i_col;
+  int max_nx = 0, max_int = 0;
+  const char *error = nullptr;
+};
+template <typename T>
+void append_chunks(std::vector<T> &dst, const std::vector<BsellChunk> &chunks, std::vector<T> BsellChunk::*member)
+{
+  size_t total = 0;
+  std::vector<size_t> at(chunks.size() + 1, 0);
+  for (size_t c = 0; c < chunks.size(); ++c) at[c + 1] = at[c] + (chunks[c].*member).size();
+  total = at[chunks.size()];
+  dst.resize(total);
+  const int64_t nch = int64_t(chunks.size());
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t c = 0; c < nch; ++c) {
+    const std::vector<T> &v = chunks[c].*member;
+    if (!v.empty()) std::memcpy(dst.data() + at[c], v.data(), v.size() * sizeof(T));
+  }
+}
+} // namespace
+
 static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<int> &colind,
                             const std::vector<int> &diagpos, const std::vector<int> &blk_ptr,
                             const std::vector<int> &colour_blk, bool lower, DevBsell &out)
 {
   const int nb = int(blk_ptr.size()) - 1;
-  std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), e_map, i_map, x_ptr(nb + 1, 0), x_ids;
-  std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
-  std::vector<int> e_gcol;           // the same entries as factor rows (kernels without staging)
-  std::vector<int> xloc(rowptr.size() - 1, -1); // factor row -> position in the current block's list
-  int max_nx = 0;
   std::vector<unsigned> e_len(nb, 0u), i_mask(nb, 0u); // i_mask: local rows that occur as an intra-block column
-  std::vector<unsigned char> e_prow(size_t(nb) * 32, 0), i_col;
+  std::vector<unsigned char> e_prow(size_t(nb) * 32, 0);
   std::vector<unsigned short> i_off(size_t(nb) * 33, 0);
-  e_col.reserve(colind.size() / 2);
-  e_map.reserve(colind.size() / 2);
-  int max_int = 0;
-  std::vector<std::pair<int, int>> tmp;
-  std::vector<std::vector<int>> ext(32); // CSR positions of the entries of each local row that leave the block
-  std::vector<int> srt(32);
-  for (int b = 0; b < nb; ++b) {
-    const int r0 = blk_ptr[b], r1 = blk_ptr[b + 1];
-    if (r1 - r0 > 32) throw StateError("bsell: block with more than 32 rows");
-    for (int lr = 0; lr < 32; ++lr) ext[lr].clear();
-    for (int r = r0; r < r1; ++r) {
-      const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
-      for (int e = a; e < z; ++e) {
-        const int c = colind[e];
-        const bool intra = lower ? (c >= r0) : (c < r1);
-        if (!intra) ext[r - r0].push_back(e);
-      }
-    }
-    // distinct outside rows in first-use order
-    for (int lr = 0; lr < 32; ++lr)
-      for (int e : ext[lr]) {
-        const int c = colind[e];
-        if (xloc[c] < 0) { xloc[c] = int(x_ids.size()) - x_ptr[b]; x_ids.push_back(c); }
-      }
-    x_ptr[b + 1] = int(x_ids.size());
-    if (x_ptr[b + 1] - x_ptr[b] > 65535) throw StateError("bsell: more than 65535 outside rows in a block");
-    max_nx = std::max(max_nx, x_ptr[b + 1] - x_ptr[b]);
-    // passes of eight rows with similar numbers of outside entries; local rows >= r1 - r0 are empty fillers
-    for (int lr = 0; lr < 32; ++lr) srt[lr] = lr;
-    std::stable_sort(srt.begin(), srt.end(), [&](int x, int y) { return ext[x].size() > ext[y].size(); });
-    unsigned lens = 0;
-    for (int q = 0; q < 4; ++q) {
-      int len = 0;
-      for (int j = 0; j < 8; ++j) len = std::max(len, (int(ext[srt[q * 8 + j]].size()) + 3) / 4);
-      if (len > 255) throw StateError("bsell: more than 1020 outside entries in a row");
-      lens |= unsigned(len) << (8 * q);
-      const size_t base = e_col.size();
-      e_col.resize(base + size_t(len) * 32, 0);
-      e_gcol.resize(base + size_t(len) * 32, 0);
-      e_map.resize(base + size_t(len) * 32, -1);
-      for (int l = 0; l < 32; ++l) {
-        const std::vector<int> &ex = ext[srt[q * 8 + l / 4]];
-        for (int k = 0; k < len; ++k) {
-          const size_t o = base + size_t(k) * 32 + l;
-          const size_t e = size_t(k) * 4 + (l & 3);
-          if (e < ex.size()) { e_col[o] = (unsigned short)xloc[colind[ex[e]]]; e_gcol[o] = colind[ex[e]]; e_map[o] = ex[e]; }
-          else { e_col[o] = 0; e_gcol[o] = x_ids[x_ptr[b]]; } // padding: value 0 times the block's first outside row
+  const int nchunks = (nb + kBsellChunk - 1) / kBsellChunk;
+  std::vector<BsellChunk> chunks(nchunks);
+#pragma omp parallel
+  {
+    // per-thread scratch
+    std::vector<int> xloc(rowptr.size() - 1, -1); // factor row -> position in the current block's list
+    std::vector<std::pair<int, int>> tmp;
+    std::vector<std::vector<int>> ext(32); // CSR positions of the entries of each local row that leave the block
+    std::vector<int> srt(32);
+#pragma omp for schedule(dynamic, 1)
+    for (int ch = 0; ch < nchunks; ++ch) {
+      BsellChunk &C = chunks[ch];
+      const int b_lo = ch * kBsellChunk, b_hi = std::min(nb, b_lo + kBsellChunk);
+      C.e_ptr.assign(b_hi - b_lo + 1, 0); C.i_ptr.assign(b_hi - b_lo + 1, 0); C.x_ptr.assign(b_hi - b_lo + 1, 0);
+      for (int b = b_lo; b < b_hi && !C.error; ++b) {
+        const int lb = b - b_lo;
+        const int r0 = blk_ptr[b], r1 = blk_ptr[b + 1];
+        if (r1 - r0 > 32) { C.error = "bsell: block with more than 32 rows"; break; }
+        for (int lr = 0; lr < 32; ++lr) ext[lr].clear();
+        for (int r = r0; r < r1; ++r) {
+          const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
+          for (int e = a; e < z; ++e) {
+            const int c = colind[e];
+            const bool intra = lower ? (c >= r0) : (c < r1);
+            if (!intra) ext[r - r0].push_back(e);
+          }
         }
+        // distinct outside rows in first-use order
+        for (int lr = 0; lr < 32; ++lr)
+          for (int e : ext[lr]) {
+            const int c = colind[e];
+            if (xloc[c] < 0) { xloc[c] = int(C.x_ids.size()) - C.x_ptr[lb]; C.x_ids.push_back(c); }
+          }
+        C.x_ptr[lb + 1] = int(C.x_ids.size());
+        const int nx = C.x_ptr[lb + 1] - C.x_ptr[lb];
+        if (nx > 65535) C.error = "bsell: more than 65535 outside rows in a block";
+        C.max_nx = std::max(C.max_nx, nx);
+        // passes of eight rows with similar numbers of outside entries; local rows >= r1 - r0 are empty fillers
+        for (int lr = 0; lr < 32; ++lr) srt[lr] = lr;
+        std::stable_sort(srt.begin(), srt.end(), [&](int x, int y) { return ext[x].size() > ext[y].size(); });
+        unsigned lens = 0;
+        for (int q = 0; q < 4 && !C.error; ++q) {
+          int len = 0;
+          for (int j = 0; j < 8; ++j) len = std::max(len, (int(ext[srt[q * 8 + j]].size()) + 3) / 4);
+          if (len > 255) { C.error = "bsell: more than 1020 outside entries in a row"; break; }
+          lens |= unsigned(len) << (8 * q);
+          const size_t base = C.e_col.size();
+          C.e_col.resize(base + size_t(len) * 32, 0);
+          C.e_gcol.resize(base + size_t(len) * 32, 0);
+          C.e_map.resize(base + size_t(len) * 32, -1);
+          for (int l = 0; l < 32; ++l) {
+            const std::vector<int> &ex = ext[srt[q * 8 + l / 4]];
+            for (int k = 0; k < len; ++k) {
+              const size_t o = base + size_t(k) * 32 + l;
+              const size_t e = size_t(k) * 4 + (l & 3);
+              if (e < ex.size()) { C.e_col[o] = (unsigned short)xloc[colind[ex[e]]]; C.e_gcol[o] = colind[ex[e]]; C.e_map[o] = ex[e]; }
+              else { C.e_col[o] = 0; C.e_gcol[o] = C.x_ids[C.x_ptr[lb]]; } // padding: value 0 times the block's first outside row
+            }
+          }
+        }
+        for (int k = C.x_ptr[lb]; k < C.x_ptr[lb + 1]; ++k) xloc[C.x_ids[k]] = -1;
+        for (int t = 0; t < 32; ++t) e_prow[size_t(b) * 32 + t] = (unsigned char)srt[t];
+        e_len[b] = lens;
+        C.e_ptr[lb + 1] = int(C.e_col.size());
+        const size_t ibase = C.i_col.size();
+        for (int lr = 0; lr < 32; ++lr) {
+          i_off[size_t(b) * 33 + lr] = (unsigned short)(C.i_col.size() - ibase);
+          const int r = r0 + lr;
+          if (r >= r1) continue;
+          const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
+          tmp.clear();
+          for (int e = a; e < z; ++e) {
+            const int c = colind[e];
+            const bool intra = lower ? (c >= r0) : (c < r1);
+            if (intra) tmp.emplace_back(c - r0, e);
+          }
+          if (!lower) std::reverse(tmp.begin(), tmp.end()); // descending columns for the backward sweep
+          for (auto &ce : tmp) { C.i_col.push_back((unsigned char)ce.first); C.i_map.push_back(ce.second); i_mask[b] |= 1u << ce.first; }
+        }
+        i_off[size_t(b) * 33 + 32] = (unsigned short)(C.i_col.size() - ibase);
+        C.max_int = std::max(C.max_int, int(C.i_col.size() - ibase));
+        C.i_ptr[lb + 1] = int(C.i_col.size());
       }
+      if (C.error) // leave the scratch clean for the next chunk of this thread
+        std::fill(xloc.begin(), xloc.end(), -1);
     }
-    for (int k = x_ptr[b]; k < x_ptr[b + 1]; ++k) xloc[x_ids[k]] = -1;
-    for (int t = 0; t < 32; ++t) e_prow[size_t(b) * 32 + t] = (unsigned char)srt[t];
-    e_len[b] = lens;
-    if (e_col.size() > size_t(0x7fffffff)) throw StateError("bsell: more than 2^31 slots");
-    e_ptr[b + 1] = int(e_col.size());
-    const size_t ibase = i_col.size();
-    for (int lr = 0; lr < 32; ++lr) {
-      i_off[size_t(b) * 33 + lr] = (unsigned short)(i_col.size() - ibase);
-      const int r = r0 + lr;
-      if (r >= r1) continue;
-      const int a = lower ? rowptr[r] : diagpos[r] + 1, z = lower ? diagpos[r] : rowptr[r + 1];
-      tmp.clear();
-      for (int e = a; e < z; ++e) {
-        const int c = colind[e];
-        const bool intra = lower ? (c >= r0) : (c < r1);
-        if (intra) tmp.emplace_back(c - r0, e);
-      }
-      if (!lower) std::reverse(tmp.begin(), tmp.end()); // descending columns for the backward sweep
-      for (auto &ce : tmp) { i_col.push_back((unsigned char)ce.first); i_map.push_back(ce.second); i_mask[b] |= 1u << ce.first; }
-    }
-    i_off[size_t(b) * 33 + 32] = (unsigned short)(i_col.size() - ibase);
-    max_int = std::max(max_int, int(i_col.size() - ibase));
-    i_ptr[b + 1] = int(i_col.size());
   }
+  for (const BsellChunk &C : chunks)
+    if (C.error) throw StateError(C.error);
+  // concatenate: per-block pointers shifted by the chunk's base
+  std::vector<int> e_ptr(nb + 1, 0), i_ptr(nb + 1, 0), x_ptr(nb + 1, 0);
+  int max_nx = 0, max_int = 0;
+  {
+    int64_t eb = 0, ib = 0, xb = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const BsellChunk &C = chunks[ch];
+      const int b_lo = ch * kBsellChunk, cnt = int(C.e_ptr.size()) - 1;
+      if (eb + int64_t(C.e_col.size()) > int64_t(0x7fffffff)) throw StateError("bsell: more than 2^31 slots");
+      for (int lb = 0; lb < cnt; ++lb) {
+        e_ptr[b_lo + lb + 1] = int(eb) + C.e_ptr[lb + 1];
+        i_ptr[b_lo + lb + 1] = int(ib) + C.i_ptr[lb + 1];
+        x_ptr[b_lo + lb + 1] = int(xb) + C.x_ptr[lb + 1];
+      }
+      eb += int64_t(C.e_col.size()); ib += int64_t(C.i_col.size()); xb += int64_t(C.x_ids.size());
+      max_nx = std::max(max_nx, C.max_nx);
+      max_int = std::max(max_int, C.max_int);
+    }
+  }
+  std::vector<int> e_map, e_gcol, i_map, x_ids;
+  std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
+  std::vector<unsigned char> i_col;
+  append_chunks(e_map, chunks, &BsellChunk::e_map);
+  append_chunks(e_gcol, chunks, &BsellChunk::e_gcol); // the same entries as factor rows (kernels without staging)
+  append_chunks(i_map, chunks, &BsellChunk::i_map);
+  append_chunks(x_ids, chunks, &BsellChunk::x_ids);
+  append_chunks(e_col, chunks, &BsellChunk::e_col);
+  append_chunks(i_col, chunks, &BsellChunk::i_col);
+  chunks.clear();
   out.n_blocks = nb;
   out.max_int = max_int;
   out.max_nx = max_nx;
