@@ -97,6 +97,44 @@ int face_local_nodes(int dim, int f, int out[6])
   return n;
 }
 
+// Rows of a pattern are built in chunks of kRowChunk consecutive rows by the host threads: every row is gathered,
+// sorted and made unique ONCE into a chunk-local buffer, the row lengths are prefix-summed and the chunk buffers are
+// copied to their place (before: two passes that sorted every row twice).  Independent of the thread count.
+namespace {
+constexpr int kRowChunk = 8192;
+template <typename GatherRow>
+void build_rows_chunked(int n_rows, Csr &out, GatherRow &&gather)
+{
+  out.rowptr.assign(size_t(n_rows) + 1, 0);
+  const int nchunks = (n_rows + kRowChunk - 1) / kRowChunk;
+  std::vector<std::vector<int>> chunk_cols(nchunks);
+#pragma omp parallel
+  {
+    std::vector<int> buf;
+#pragma omp for schedule(dynamic, 1)
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int r_lo = ch * kRowChunk, r_hi = std::min(n_rows, r_lo + kRowChunk);
+      std::vector<int> &cols = chunk_cols[ch];
+      for (int r = r_lo; r < r_hi; ++r) {
+        buf.clear();
+        gather(r, buf);
+        std::sort(buf.begin(), buf.end());
+        const int n = int(std::unique(buf.begin(), buf.end()) - buf.begin());
+        out.rowptr[r + 1] = n;
+        cols.insert(cols.end(), buf.begin(), buf.begin() + n);
+      }
+    }
+  }
+  for (int r = 0; r < n_rows; ++r) out.rowptr[r + 1] += out.rowptr[r];
+  out.colind.resize(size_t(out.rowptr[n_rows]));
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const std::vector<int> &cols = chunk_cols[ch];
+    if (!cols.empty()) std::memcpy(&out.colind[out.rowptr[size_t(ch) * kRowChunk]], cols.data(), sizeof(int) * cols.size());
+  }
+}
+} // namespace
+
 void build_pattern(int64_t nc, const int *cell_rows, int kr, const int *cell_cols, int kc, int n_rows_total,
                    int n_rows_owned, int n_cols, Csr &out)
 {
@@ -113,79 +151,25 @@ void build_pattern(int64_t nc, const int *cell_rows, int kr, const int *cell_col
   }
   out.n_rows = n_rows_owned;
   out.n_cols = n_cols;
-  out.rowptr.assign(size_t(n_rows_owned) + 1, 0);
-#pragma omp parallel
-  {
-    std::vector<int> buf;
-#pragma omp for schedule(static)
-    for (int r = 0; r < n_rows_owned; ++r) {
-      buf.clear();
-      for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
-        const int *cc = &cell_cols[int64_t(r2c[k]) * kc];
-        buf.insert(buf.end(), cc, cc + kc);
-      }
-      std::sort(buf.begin(), buf.end());
-      out.rowptr[r + 1] = int(std::unique(buf.begin(), buf.end()) - buf.begin());
+  build_rows_chunked(n_rows_owned, out, [&](int r, std::vector<int> &buf) {
+    for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
+      const int *cc = &cell_cols[int64_t(r2c[k]) * kc];
+      buf.insert(buf.end(), cc, cc + kc);
     }
-  }
-  for (int r = 0; r < n_rows_owned; ++r) out.rowptr[r + 1] += out.rowptr[r];
-  out.colind.resize(out.rowptr[n_rows_owned]);
-#pragma omp parallel
-  {
-    std::vector<int> buf;
-#pragma omp for schedule(static)
-    for (int r = 0; r < n_rows_owned; ++r) {
-      buf.clear();
-      for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
-        const int *cc = &cell_cols[int64_t(r2c[k]) * kc];
-        buf.insert(buf.end(), cc, cc + kc);
-      }
-      std::sort(buf.begin(), buf.end());
-      const int n = int(std::unique(buf.begin(), buf.end()) - buf.begin());
-      std::memcpy(&out.colind[out.rowptr[r]], buf.data(), sizeof(int) * n);
-    }
-  }
+  });
 }
 
 void symbolic_product(const Csr &A, const Csr &B, Csr &out)
 {
   out.n_rows = A.n_rows;
   out.n_cols = B.n_cols;
-  out.rowptr.assign(size_t(A.n_rows) + 1, 0);
-  std::vector<std::vector<int>> rows; // filled in two passes to keep memory bounded
-#pragma omp parallel
-  {
-    std::vector<int> buf;
-#pragma omp for schedule(static)
-    for (int i = 0; i < A.n_rows; ++i) {
-      buf.clear();
-      for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
-        const int k = A.colind[p];
-        if (k >= B.n_rows) continue; // ghost row of B not available locally
-        buf.insert(buf.end(), B.colind.begin() + B.rowptr[k], B.colind.begin() + B.rowptr[k + 1]);
-      }
-      std::sort(buf.begin(), buf.end());
-      out.rowptr[i + 1] = int(std::unique(buf.begin(), buf.end()) - buf.begin());
+  build_rows_chunked(A.n_rows, out, [&](int i, std::vector<int> &buf) {
+    for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+      const int k = A.colind[p];
+      if (k >= B.n_rows) continue; // ghost row of B not available locally
+      buf.insert(buf.end(), B.colind.begin() + B.rowptr[k], B.colind.begin() + B.rowptr[k + 1]);
     }
-  }
-  for (int i = 0; i < A.n_rows; ++i) out.rowptr[i + 1] += out.rowptr[i];
-  out.colind.resize(out.rowptr[A.n_rows]);
-#pragma omp parallel
-  {
-    std::vector<int> buf;
-#pragma omp for schedule(static)
-    for (int i = 0; i < A.n_rows; ++i) {
-      buf.clear();
-      for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
-        const int k = A.colind[p];
-        if (k >= B.n_rows) continue;
-        buf.insert(buf.end(), B.colind.begin() + B.rowptr[k], B.colind.begin() + B.rowptr[k + 1]);
-      }
-      std::sort(buf.begin(), buf.end());
-      const int n = int(std::unique(buf.begin(), buf.end()) - buf.begin());
-      std::memcpy(&out.colind[out.rowptr[i]], buf.data(), sizeof(int) * n);
-    }
-  }
+  });
 }
 
 // Recursive coordinate bisection of cell centroids (replaces GridTools::partition_triangulation /

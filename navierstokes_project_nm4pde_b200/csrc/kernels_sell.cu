@@ -720,6 +720,11 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
       BsellChunk &C = chunks[ch];
       const int b_lo = ch * kBsellChunk, b_hi = std::min(nb, b_lo + kBsellChunk);
       C.e_ptr.assign(b_hi - b_lo + 1, 0); C.i_ptr.assign(b_hi - b_lo + 1, 0); C.x_ptr.assign(b_hi - b_lo + 1, 0);
+      { // one allocation per array instead of repeated growth (large reallocations serialise on the page tables)
+        const size_t nnz_chunk = size_t(rowptr[blk_ptr[b_hi]] - rowptr[blk_ptr[b_lo]]);
+        C.e_col.reserve(nnz_chunk); C.e_gcol.reserve(nnz_chunk); C.e_map.reserve(nnz_chunk);
+        C.i_col.reserve(nnz_chunk / 2); C.i_map.reserve(nnz_chunk / 2); C.x_ids.reserve(nnz_chunk / 2);
+      }
       for (int b = b_lo; b < b_hi && !C.error; ++b) {
         const int lb = b - b_lo;
         const int r0 = blk_ptr[b], r1 = blk_ptr[b + 1];

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 
 #include "nsb_internal.hpp"
@@ -269,8 +270,10 @@ template <typename T>
 static std::vector<T> interleave32(const std::vector<T> &in, int64_t nc, int64_t nc_pad, int k, T pad)
 { // [nc][k] -> [nc_pad/32][k][32]
   std::vector<T> out(size_t(nc_pad) * k, pad);
-  for (int64_t c = 0; c < nc; ++c)
-    for (int j = 0; j < k; ++j) out[((c >> 5) * k + j) * 32 + (c & 31)] = in[c * k + j];
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < nc_pad / 32; ++g) // one group of 32 cells = one contiguous piece of `out`
+    for (int64_t c = g * 32; c < std::min(nc, g * 32 + 32); ++c)
+      for (int j = 0; j < k; ++j) out[(g * k + j) * 32 + (c & 31)] = in[c * k + j];
   return out;
 }
 
@@ -311,17 +314,35 @@ static void finalize_setup(Handle &H)
   for (int i = 0; i < H.n_nodes_owned; ++i) diag[i] = find_in_row(H.hFs, i, i);
   H.d_diagF.upload(diag);
   {
-    std::vector<int> map(size_t(H.nc_pad) * n2 * n2, -1);
+    // [nc_pad / 32][n2 * n2][32] positions in F_s, -1 for padding cells and ghost rows.  1.9 GB at 4.7 M tetrahedra:
+    // every group of 32 cells (one contiguous piece) is initialised and filled by the thread that owns it; the n2
+    // columns of a cell are sorted once and every row of F_s is walked once (merge) instead of n2 binary searches
+    const size_t gsz = size_t(n2) * n2 * 32;
+    std::unique_ptr<int[]> map(new int[size_t(H.nc_pad / 32) * gsz]);
 #pragma omp parallel for schedule(static)
-    for (int64_t c = 0; c < nc; ++c) {
-      const int *cn = &H.h_cell_nodes[c * n2];
-      for (int i = 0; i < n2; ++i) {
-        if (cn[i] >= H.n_nodes_owned) continue;
-        for (int j = 0; j < n2; ++j)
-          map[((c >> 5) * (n2 * n2) + i * n2 + j) * 32 + (c & 31)] = find_in_row(H.hFs, cn[i], cn[j]);
+    for (int64_t g = 0; g < H.nc_pad / 32; ++g) {
+      int *mg = map.get() + size_t(g) * gsz;
+      std::fill(mg, mg + gsz, -1);
+      for (int64_t c = g * 32; c < std::min<int64_t>(nc, g * 32 + 32); ++c) {
+        const int *cn = &H.h_cell_nodes[c * n2];
+        int sj[10], sc[10]; // local column indices sorted by node id
+        for (int j = 0; j < n2; ++j) sj[j] = j;
+        std::sort(sj, sj + n2, [&](int a, int b) { return cn[a] < cn[b]; });
+        for (int j = 0; j < n2; ++j) sc[j] = cn[sj[j]];
+        for (int i = 0; i < n2; ++i) {
+          if (cn[i] >= H.n_nodes_owned) continue;
+          int *mi = mg + size_t(i) * n2 * 32 + (c & 31);
+          int e = H.hFs.rowptr[cn[i]];
+          const int e1 = H.hFs.rowptr[cn[i] + 1];
+          for (int j = 0; j < n2; ++j) {
+            if (j > 0 && sc[j] == sc[j - 1]) { mi[size_t(sj[j]) * 32] = mi[size_t(sj[j - 1]) * 32]; continue; }
+            while (e < e1 && H.hFs.colind[e] < sc[j]) ++e;
+            mi[size_t(sj[j]) * 32] = (e < e1 && H.hFs.colind[e] == sc[j]) ? e : -1;
+          }
+        }
       }
     }
-    H.d_mapF.upload(map);
+    H.d_mapF.upload(map.get(), size_t(H.nc_pad / 32) * gsz);
   }
   phase("uploads, scatter map");
   H.d_vcoords.upload(interleave32<double>(H.h_vcoords, nc, H.nc_pad, nv1 * dim, 0.0));

@@ -117,12 +117,13 @@ struct DevBuf {
     if (g_dry.on) { g_dry.record(0xA110C, &count, sizeof(count)); return; }
     if (count) NSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
   }
-  void upload(const std::vector<T> &h)
+  void upload(const T *h, size_t count)
   {
-    if (g_dry.on) { n = h.size(); g_dry.record(sizeof(T), h.data(), h.size() * sizeof(T)); return; }
-    if (n != h.size()) alloc(h.size());
-    if (n) NSB_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    if (g_dry.on) { n = count; g_dry.record(sizeof(T), h, count * sizeof(T)); return; }
+    if (n != count) alloc(count);
+    if (n) NSB_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
   }
+  void upload(const std::vector<T> &h) { upload(h.data(), h.size()); }
   void zero(cudaStream_t s = 0)
   {
     if (g_dry.on) return;
