@@ -73,6 +73,7 @@ void number_dofs(const Mesh &M, Dofs &D)
   const int n_u = dim * n_nodes;
   D.cell_dofs.resize(size_t(D.nc) * D.dpc);
   D.cell_coords.resize(size_t(D.nc) * nv1 * dim);
+#pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < D.nc; ++c) {
     int *cd = &D.cell_dofs[c * D.dpc];
     const int *cn = &D.cell_nodes[c * D.n2];
