@@ -277,6 +277,31 @@ static std::vector<T> interleave32(const std::vector<T> &in, int64_t nc, int64_t
   return out;
 }
 
+// dry run only: the host-side members of the setup structures (launch geometry, colour / level boundaries) join
+// the fingerprint after the uploads
+static void dry_record_host_state(Handle &H)
+{
+  auto rec_vec = [](const std::vector<int> &v) { g_dry.record(0x4057, v.data(), v.size() * sizeof(int)); };
+  auto rec_i64 = [](std::initializer_list<int64_t> v) { g_dry.record(0x4058, v.begin(), v.size() * sizeof(int64_t)); };
+  auto rec_sell = [&](const DevSell &S) {
+    rec_i64({S.n_slices, S.lanes, S.n_slots});
+    rec_vec(S.range_slice);
+  };
+  auto rec_bsell = [&](const DevBsell &B) {
+    rec_i64({B.n_blocks, B.max_int, B.max_nx, B.n_ext, B.n_int});
+    rec_vec(B.col_max_nx);
+  };
+  rec_i64({H.n_blk_Fs, H.n_blk_S, H.nc_pad});
+  rec_sell(H.sellF);
+  for (const DevIlu *ilu : {&H.iluF, &H.iluS}) {
+    rec_i64({ilu->n, ilu->bs_rhs, ilu->nnz, ilu->stream, ilu->sell, ilu->bsell, ilu->sdmode});
+    rec_vec(ilu->h_order); rec_vec(ilu->colour_blk); rec_vec(ilu->colour_ptr); rec_vec(ilu->cblkL); rec_vec(ilu->cblkU);
+    rec_vec(ilu->lvl_ptr_f); rec_vec(ilu->lvl_ptr_b);
+    rec_sell(ilu->sellL); rec_sell(ilu->sellU);
+    rec_bsell(ilu->bL); rec_bsell(ilu->bU);
+  }
+}
+
 // nsb_finalize_setup: everything static is built on the host here and uploaded (the dry run of
 // nsb_debug_setup_fingerprint hashes the uploads instead)
 static void finalize_setup(Handle &H)
@@ -397,6 +422,7 @@ static void finalize_setup(Handle &H)
   phase("ILU schedule S");
   solver_alloc(H);
   NSB_CUDA_SETUP(cudaDeviceSynchronize());
+  if (g_dry.on) dry_record_host_state(H);
   H.finalized = true;
   H.assembled = H.prec_ready = false;
 }
