@@ -210,18 +210,21 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
     const int *rs = &rows[slices[i].first];
     const size_t base = size_t(off[i]);
     const int len = int((off[i + 1] - off[i]) / 32);
+    int rl_of[32], pad_of[32], rp_of[32];
     for (int l = 0; l < 32; ++l) {
-      const int r = l / lanes < ns ? rs[l / lanes] : -1, q = l % lanes;
+      const int r = l / lanes < ns ? rs[l / lanes] : -1;
       rowid[size_t(i) * 32 + l] = r;
-      const int rl = r >= 0 ? rowptr[r + 1] - rowptr[r] : 0;
-      const int pad_col = (r >= 0 && rl > 0) ? colind[rowptr[r]] : 0;
-      for (int k = 0; k < len; ++k) {
-        const size_t o = base + size_t(k) * 32 + l;
-        const int e = k * lanes + q;
-        if (e < rl) { col[o] = colind[rowptr[r] + e]; map[o] = src.empty() ? rowptr[r] + e : src[rowptr[r] + e]; }
-        else { col[o] = pad_col; map[o] = -1; }
-      }
+      rp_of[l] = r >= 0 ? rowptr[r] : 0;
+      rl_of[l] = r >= 0 ? rowptr[r + 1] - rowptr[r] : 0;
+      pad_of[l] = (r >= 0 && rl_of[l] > 0) ? colind[rowptr[r]] : 0;
     }
+    for (int k = 0; k < len; ++k) // slot order = memory order
+      for (int l = 0; l < 32; ++l) {
+        const size_t o = base + size_t(k) * 32 + l;
+        const int e = k * lanes + l % lanes;
+        if (e < rl_of[l]) { col[o] = colind[rp_of[l] + e]; map[o] = src.empty() ? rp_of[l] + e : src[rp_of[l] + e]; }
+        else { col[o] = pad_of[l]; map[o] = -1; }
+      }
   }
   out.range_slice.back() = int(nsl);
   out.n_slices = int(nsl);
