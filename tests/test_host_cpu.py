@@ -56,6 +56,28 @@ def test_generators_and_numbering(gen, dim, ids):
     assert (np.linalg.det(J) > 0).all()
 
 
+@pytest.mark.parametrize("gen", [lambda: HostMesh.cylinder2d(2), lambda: HostMesh.cylinder3d(1, 4), lambda: HostMesh.cube(4),
+                                 lambda: HostMesh.box(2, [3, 5], [0, 0], [1, 2])])
+def test_boundary_faces_against_a_brute_force_search(gen):
+    """Mesh::build_boundary (faces bucketed by their smallest vertex, buckets searched in parallel): the faces that
+    belong to exactly one cell, in (cell, local face) order, vertices ascending -- against numpy's unique()."""
+    m = gen()
+    dim, cells = m.dim, m.cells
+    faces, owner = [], []
+    for c in range(cells.shape[0]):
+        for f in range(dim + 1):  # local face f = the face opposite to local vertex f
+            faces.append(sorted(int(v) for k, v in enumerate(cells[c]) if k != f))
+            owner.append(c)
+    faces, owner = np.array(faces), np.array(owner)
+    _, inv, cnt = np.unique(faces, axis=0, return_inverse=True, return_counts=True)
+    single = cnt[inv.ravel()] == 1
+    assert np.array_equal(m.bfaces, faces[single]) and np.array_equal(m.bface_cells, owner[single])
+    # a closed surface: every (dim-2)-dimensional sub-face of the boundary is shared by exactly two boundary faces
+    sub = np.concatenate([np.delete(m.bfaces, k, axis=1) for k in range(dim)])
+    _, c2 = np.unique(np.sort(sub, axis=1), axis=0, return_counts=True)
+    assert (c2 == 2).all()
+
+
 def test_msh_roundtrip(tmp_path):
     """GridIn::read_msh replacement: Gmsh v2 ASCII written and read back keeps cells, vertices and ids."""
     m = HostMesh.cylinder2d(1)
