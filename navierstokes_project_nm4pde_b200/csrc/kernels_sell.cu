@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <numeric>
 
+#include <memory>
+
 #include "nsb_internal.hpp"
 
 namespace nsb {
@@ -160,6 +162,13 @@ __global__ void k_pad3(int n_nodes, int n_owned, int goff, const double *__restr
 void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
                 const std::vector<int> &ranges, int window, int lanes, DevSell &out)
 {
+  sell_build(rowptr, colind.data(), src.empty() ? nullptr : src.data(), ranges, window, lanes, out);
+}
+
+// colind / src as plain arrays (src may be null: the entries are numbered as in rowptr / colind)
+void sell_build(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges, int window,
+                int lanes, DevSell &out)
+{
   out.range_slice.assign(ranges.size(), 0);
   out.lanes = lanes;
   const int R = 32 / lanes; // rows per slice
@@ -202,8 +211,10 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
   if (off[nsl] > int64_t(0x7fffffff)) throw StateError("SELL: more than 2^31 slots");
   for (int64_t i = 0; i <= nsl; ++i) slice_ptr[i] = int(off[i]);
   // 3. fill the slices
+  // (uninitialised storage: every element is written below, by the thread that touches its pages first --
+  // zero-filling 1.5 GB of std::vector on one thread cost more than the fill itself)
   const size_t n_slots = size_t(off[nsl]);
-  std::vector<int> rowid(size_t(nsl) * 32), col(n_slots), map(n_slots);
+  std::unique_ptr<int[]> rowid(new int[size_t(nsl) * 32 + 1]), col(new int[n_slots + 1]), map(new int[n_slots + 1]);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < nsl; ++i) {
     const int ns = slices[i].ns;
@@ -222,18 +233,18 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
       for (int l = 0; l < 32; ++l) {
         const size_t o = base + size_t(k) * 32 + l;
         const int e = k * lanes + l % lanes;
-        if (e < rl_of[l]) { col[o] = colind[rp_of[l] + e]; map[o] = src.empty() ? rp_of[l] + e : src[rp_of[l] + e]; }
+        if (e < rl_of[l]) { col[o] = colind[rp_of[l] + e]; map[o] = src ? src[rp_of[l] + e] : rp_of[l] + e; }
         else { col[o] = pad_of[l]; map[o] = -1; }
       }
   }
   out.range_slice.back() = int(nsl);
   out.n_slices = int(nsl);
-  out.n_slots = int64_t(col.size());
+  out.n_slots = int64_t(n_slots);
   out.slice_ptr.upload(slice_ptr);
-  out.rowid.upload(rowid);
-  out.col.upload(col);
-  out.map.upload(map);
-  out.val.alloc(col.size());
+  out.rowid.upload(rowid.get(), size_t(nsl) * 32);
+  out.col.upload(col.get(), n_slots);
+  out.map.upload(map.get(), n_slots);
+  out.val.alloc(n_slots);
 }
 
 void sell_fill(Handle &H, DevSell &S, const double *src)
@@ -685,18 +696,24 @@ struct BsellChunk {
   const char *error = nullptr;
 };
 template <typename T>
-void append_chunks(std::vector<T> &dst, const std::vector<BsellChunk> &chunks, std::vector<T> BsellChunk::*member)
+struct RawArray { // uninitialised storage, filled by append_chunks
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+};
+template <typename T>
+void append_chunks(RawArray<T> &dst, const std::vector<BsellChunk> &chunks, std::vector<T> BsellChunk::*member)
 {
-  size_t total = 0;
   std::vector<size_t> at(chunks.size() + 1, 0);
   for (size_t c = 0; c < chunks.size(); ++c) at[c + 1] = at[c] + (chunks[c].*member).size();
-  total = at[chunks.size()];
-  dst.resize(total);
+  dst.n = at[chunks.size()];
+  dst.p.reset(new T[dst.n + 1]); // pages first touched by the copying threads
   const int64_t nch = int64_t(chunks.size());
 #pragma omp parallel for schedule(dynamic, 1)
   for (int64_t c = 0; c < nch; ++c) {
     const std::vector<T> &v = chunks[c].*member;
-    if (!v.empty()) std::memcpy(dst.data() + at[c], v.data(), v.size() * sizeof(T));
+    if (!v.empty()) std::memcpy(dst.p.get() + at[c], v.data(), v.size() * sizeof(T));
   }
 }
 } // namespace
@@ -822,9 +839,9 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
       max_int = std::max(max_int, C.max_int);
     }
   }
-  std::vector<int> e_map, e_gcol, i_map, x_ids;
-  std::vector<unsigned short> e_col; // index into the block's list of distinct outside rows
-  std::vector<unsigned char> i_col;
+  RawArray<int> e_map, e_gcol, i_map, x_ids;
+  RawArray<unsigned short> e_col; // index into the block's list of distinct outside rows
+  RawArray<unsigned char> i_col;
   append_chunks(e_map, chunks, &BsellChunk::e_map);
   append_chunks(e_gcol, chunks, &BsellChunk::e_gcol); // the same entries as factor rows (kernels without staging)
   append_chunks(i_map, chunks, &BsellChunk::i_map);
@@ -845,13 +862,15 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
                  lower ? "L" : "U", nb, e_col.size(), double(e_col.size()) / std::max(1, blk_ptr[nb]), i_col.size(), x_ids.size(),
                  max_nx, max_int);
   out.x_ptr.upload(x_ptr);
-  out.x_ids.upload(x_ids.empty() ? std::vector<int>(1, 0) : x_ids);
+  if (x_ids.empty()) out.x_ids.upload(std::vector<int>(1, 0));
+  else out.x_ids.upload(x_ids.p.get(), x_ids.n);
   out.n_ext = int64_t(e_col.size());
   out.n_int = int64_t(i_col.size());
-  out.e_ptr.upload(e_ptr); out.e_lix.upload(e_col); out.e_col.upload(e_gcol); out.e_map.upload(e_map);
+  out.e_ptr.upload(e_ptr); out.e_lix.upload(e_col.p.get(), e_col.n); out.e_col.upload(e_gcol.p.get(), e_gcol.n);
+  out.e_map.upload(e_map.p.get(), e_map.n);
   out.e_len.upload(e_len); out.e_prow.upload(e_prow);
   out.e_val.alloc(e_col.size());
-  out.i_ptr.upload(i_ptr); out.i_map.upload(i_map); out.i_off.upload(i_off); out.i_col.upload(i_col);
+  out.i_ptr.upload(i_ptr); out.i_map.upload(i_map.p.get(), i_map.n); out.i_off.upload(i_off); out.i_col.upload(i_col.p.get(), i_col.n);
   out.i_mask.upload(i_mask);
   out.i_val.alloc(i_col.size());
 }

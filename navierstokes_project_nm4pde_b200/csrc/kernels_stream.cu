@@ -16,6 +16,8 @@
 
 #include <cstdlib>
 
+#include <memory>
+
 #include "nsb_internal.hpp"
 
 namespace nsb {
@@ -233,13 +235,14 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
                       const std::vector<int> &diagpos, const std::vector<int> &colour_ptr)
 {
   const int n = ilu.n;
-  std::vector<int> Lp(n + 1, 0), Up(n + 1, 0), Lc, Uc, mapL, mapU;
+  std::vector<int> Lp(n + 1, 0), Up(n + 1, 0);
   for (int k = 0; k < n; ++k) {
     Lp[k + 1] = Lp[k] + (diagpos[k] - rowptr[k]);
     Up[k + 1] = Up[k] + (rowptr[k + 1] - diagpos[k] - 1);
   }
-  Lc.resize(size_t(Lp[n])); mapL.resize(size_t(Lp[n]));
-  Uc.resize(size_t(Up[n])); mapU.resize(size_t(Up[n]));
+  // uninitialised storage, first touched by the filling threads
+  const size_t nL = size_t(Lp[n]), nU = size_t(Up[n]);
+  std::unique_ptr<int[]> Lc(new int[nL + 1]), mapL(new int[nL + 1]), Uc(new int[nU + 1]), mapU(new int[nU + 1]);
 #pragma omp parallel for schedule(static)
   for (int k = 0; k < n; ++k) {
     int o = Lp[k];
@@ -262,15 +265,15 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
   }
   ilu.cblkL[nc] = int(bL.size());
   ilu.cblkU[nc] = int(bU.size());
-  ilu.Lp.upload(Lp); ilu.Lc.upload(Lc); ilu.mapL.upload(mapL);
-  ilu.Up.upload(Up); ilu.Uc.upload(Uc); ilu.mapU.upload(mapU);
-  ilu.Lv.alloc(Lc.size()); ilu.Uv.alloc(Uc.size());
+  ilu.Lp.upload(Lp); ilu.Lc.upload(Lc.get(), nL); ilu.mapL.upload(mapL.get(), nL);
+  ilu.Up.upload(Up); ilu.Uc.upload(Uc.get(), nU); ilu.mapU.upload(mapU.get(), nU);
+  ilu.Lv.alloc(nL); ilu.Uv.alloc(nU);
   ilu.blkL.upload(bL); ilu.blkU.upload(bU);
   ilu.stream = true;
   ilu.sell = false;
   if (ilu.bs_rhs == 3) { // SELL-32 copies of the factors for the 3-component solves
-    sell_build(Lp, Lc, mapL, colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellL);
-    sell_build(Up, Uc, mapU, colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellU);
+    sell_build(Lp, Lc.get(), mapL.get(), colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellL);
+    sell_build(Up, Uc.get(), mapU.get(), colour_ptr, sell_window(), sell_lanes_for(n), ilu.sellU);
     ilu.sell = true;
   }
   (void)H;

@@ -478,6 +478,8 @@ void stream_trsv(Handle &H, DevIlu &ilu, double *y, cudaStream_t s);
 // ---------------------------------------------------------------- kernels_sell.cu
 void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &src,
                 const std::vector<int> &ranges, int window, int lanes, DevSell &out);
+void sell_build(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges, int window,
+                int lanes, DevSell &out);
 int sell_lanes_for(int n_rows);
 void sell_fill(Handle &H, DevSell &S, const double *src);
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);
