@@ -8,7 +8,8 @@ import sys
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
-from test_setup_fingerprint import CASES, ORDERINGS, fingerprint, owned_prefix  # noqa: E402
+from test_setup_fingerprint import (CASES, LOCAL_CASES, LOCAL_ORDERINGS, ORDERINGS, fingerprint, fingerprint_local,
+                                    owned_prefix)  # noqa: E402
 
 out = {}
 for name, make in CASES.items():
@@ -17,6 +18,11 @@ for name, make in CASES.items():
         out[f"{name}/{o1}/{o2}"] = fingerprint(mesh, o1, o2)
         if o1 != 3:
             out[f"{name}/{o1}/{o2}/ghosts"] = fingerprint(mesh, o1, o2, owned_prefix(mesh))
+for name, nranks in LOCAL_CASES:
+    mesh = CASES[name]()
+    for rank in range(nranks):
+        for o1, o2 in LOCAL_ORDERINGS:
+            out[f"local/{name}/{nranks}/{rank}/{o1}/{o2}"] = fingerprint_local(mesh, nranks, rank, o1, o2)
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "setup_fingerprints.json"), "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
 print(len(out), "fingerprints written")

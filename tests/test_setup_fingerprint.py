@@ -57,6 +57,41 @@ def test_setup_structures_match_the_pinned_fingerprints(name):
             assert fingerprint(mesh, o1, o2, owned_prefix(mesh)) == golden[f"{name}/{o1}/{o2}/ghosts"], (name, o1, o2)
 
 
+# real subdomains: (mesh, ranks); every rank's local problem from distributed.build_local_problem
+LOCAL_CASES = (("cyl3d(2,8)", 2), ("cyl2d(8)", 3))
+LOCAL_ORDERINGS = ((1, -1), (2, 1), (1, 2))
+
+
+def fingerprint_local(mesh, nranks, rank, o1, o2):
+    """What rank `rank` of `nranks` hands to nsb_set_mesh (owned + ghost cells, owned DoFs first)."""
+    from navierstokes_project_nm4pde_b200.distributed import build_local_problem
+
+    d = HostDofs(mesh)
+    loc = build_local_problem(d.dim, d.cell_dofs(copy=False), d.cell_coords(copy=False), d.n_nodes, d.n_p,
+                              mesh.partition(nranks), nranks, rank)
+    cc = np.ascontiguousarray(loc["cell_coords"], dtype=np.float64)
+    cd = np.ascontiguousarray(loc["cell_dofs"], dtype=np.int32)
+    cap = 4096
+    out, n = np.zeros(cap, np.uint64), C.c_int32(0)
+    rc = _lib.lib().nsb_debug_setup_fingerprint(d.dim, cd.shape[0], dptr(cc), iptr(cd), d.dim * loc["node_gid"].size,
+                                                loc["p_gid"].size, d.dim * loc["n_nodes_owned"], loc["n_p_owned"], o1, o2,
+                                                out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n))
+    assert rc == 0 and 0 < n.value <= cap
+    return [hashlib.sha256(out[: n.value].tobytes()).hexdigest()[:16], int(n.value)]
+
+
+@pytest.mark.parametrize("name,nranks", LOCAL_CASES)
+def test_subdomain_structures_match_the_pinned_fingerprints(name, nranks):
+    """The same pin for what every rank of a multi-rank run builds (block-Jacobi ILU of the owned rows, ghost
+    columns dropped from the factors, ghost rows absent from the scatter map)."""
+    with open(GOLDEN) as f:
+        golden = json.load(f)
+    mesh = CASES[name]()
+    for rank in range(nranks):
+        for o1, o2 in LOCAL_ORDERINGS:
+            assert fingerprint_local(mesh, nranks, rank, o1, o2) == golden[f"local/{name}/{nranks}/{rank}/{o1}/{o2}"]
+
+
 def test_setup_structures_do_not_depend_on_the_thread_count():
     """The parallel host code must build the same arrays on 1 and on 3 threads (OpenMP schedules differ)."""
     code = ("import json, sys; sys.path[:0] = [%r, %r]; from test_setup_fingerprint import *; m = CASES['cyl3d(2,8)']();"
