@@ -364,20 +364,31 @@ def run_gpu(args):
     barrier()
     t0 = time.perf_counter()
     planned, slowest = steps, 0.0
+    failure = None
     for i in range(planned):
         ts = time.perf_counter()
-        its.append(run.step())
+        try:
+            its.append(run.step())
+        except Exception as ex:  # noqa: BLE001  (e.g. SolverControl::NoConvergence of an inner solve: the same scalars decide
+            # on every rank, so all ranks arrive here together); the steps finished so far are still a measurement
+            failure = f"step {i + 1} of the timed region raised {type(ex).__name__}: {ex}"
+            log(failure)
+            if not its:
+                raise
+            steps = len(its)
+            break
         t_prec.append(e.stat("t_prec_ms") * 1e-3); t_solve.append(e.stat("t_solve_ms") * 1e-3)
         # a step can cost twice the warm-up estimate (230-700 outer iterations): stop early rather than overrun the
         # budget (every rank takes the same decision; step_host has already synchronised, so this adds no device wait)
-        slowest = max(slowest, time.perf_counter() - ts)
+        t_last_ok = time.perf_counter()
+        slowest = max(slowest, t_last_ok - ts)
         over = float((time.perf_counter() - _T0) + extras_s + slowest > budget)
         if i + 1 < planned and reduce(over) > 0.0:
             steps = i + 1
             log(f"budget {budget:.0f} s: stopping after {steps} of {planned} planned steps (slowest step {slowest:.1f} s)")
             break
     torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    wall_ms = ((t_last_ok if failure else time.perf_counter()) - t0) * 1e3  # a failed step is not part of the measurement
     dev_ms = e.stat("t_step_dev_ms_reset")
     barrier()
     launches = e.launch_count(reset=True)
@@ -397,9 +408,15 @@ def run_gpu(args):
                 "spmv_S": stats["cnt_spmv_S"], "assemble_step": 1.0, "spmv_system": stats["n_vmult"]}
     kern = {}
     for name, cnt in per_step.items():
-        kms, kbytes = e.bench_kernel(name, iters=5, flush_l2=True)
+        try:
+            kms, kbytes = e.bench_kernel(name, iters=5, flush_l2=True)
+        except Exception as ex:  # noqa: BLE001  (a kernel that cannot be timed alone must not cost the whole line)
+            log(f"bench_kernel({name}) failed: {ex}")
+            continue
         kern[name] = dict(ms=kms, bytes=kbytes, gbs=kbytes / (kms * 1e-3) / 1e9, calls_last_step=cnt,
                           share_last_step=cnt * kms / (1e3 * (t_prec[-1] + t_solve[-1]) + 1e-9))
+    if not kern:
+        raise RuntimeError("no kernel of the step could be timed in isolation")
     dom = max(kern, key=lambda k: kern[k]["share_last_step"])
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     # (profiles/r02_traffic.json; only valid for the workload / rank count / ordering it was captured on)
@@ -436,7 +453,7 @@ def run_gpu(args):
                            partition=f"{world} subdomain(s), coordinate bisection",
                            transport=(getattr(prob, "transport", "none") if world > 1 else "none")),
                e2e=e2e, roofline=roofline, clocks=clocks,
-               detail=dict(outer_iterations=its, steps_requested=args.steps, truncated=bool(steps < args.steps),
+               detail=dict(outer_iterations=its, steps_requested=args.steps, truncated=bool(steps < args.steps), failure=failure,
                            start_up_iterations=its_prep, start_up_s=prep_s, warmup_iterations=warm_its,
                            warmup_s=[round(x, 2) for x in warm_s], setup_s=setup_s, t_prec_s=t_prec, t_solve_s=t_solve,
                            last_step_counts=stats, wall_ms_per_step=wall_ms / steps,
@@ -471,9 +488,12 @@ def run_gpu(args):
                 out["detail"]["same_mesh"] = dict(error=str(ex))
         left = budget - (time.perf_counter() - _T0)
         if not args.no_cpu_baseline and left > 45:
-            cpu = run_cpu(sample, 1, 0)
-            out["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind="port",
-                                       sample=cpu["sample"], seconds=cpu["seconds"], outer_iterations=cpu["iterations"])
+            try:
+                cpu = run_cpu(sample, 1, 0)
+                out["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind="port",
+                                           sample=cpu["sample"], seconds=cpu["seconds"], outer_iterations=cpu["iterations"])
+            except Exception as ex:  # noqa: BLE001
+                out["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cores, kind="port", sample=f"failed: {ex}")
         elif not args.no_cpu_baseline:
             out["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cores, kind="port",
                                        sample="skipped: wall-clock budget of the run exhausted (see --impl reference)")
