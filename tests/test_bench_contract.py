@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -41,3 +43,112 @@ def test_reference_arm_2d_sample():
     d = json.loads(r.stdout.strip())
     assert d["config"]["variant"] == "NavierStokes2D" and d["config"]["preconditioner"] == "asimple"
     assert d["config"]["sample_of"] == "cyl2d-2M" and d["steps"] == 2 and d["value"] > 0
+
+
+# ---- the GPU arm's host logic with a fake engine (no device): budget guard, failure handling, the JSON line ----------
+class _FakeEngine:
+    def __init__(self, fail_at=None):
+        self.calls, self.fail_at, self.dev_ms = 0, fail_at, 0.0
+
+    def launch_count(self, reset=False):
+        return 1234
+
+    def stat(self, key):
+        if key == "t_step_dev_ms_reset":
+            v, self.dev_ms = self.dev_ms, 0.0
+            return v
+        return {"t_prec_ms": 2.0, "t_solve_ms": 8.0}.get(key, 7.0)
+
+    def bench_kernel(self, name, iters=5, flush_l2=True):
+        if name == "spmv_S":
+            raise RuntimeError("cannot be timed alone")
+        return 1.0, 2.0e9
+
+
+def _fake_gpurun(bench, step_s, fail_at=None, slow_after=None):
+    import time as _time
+
+    class FakeRun:
+        def __init__(self, workload, args, world, rank, local_rank, uid=None):
+            import types
+
+            self.e = _FakeEngine()
+            self.mesh = types.SimpleNamespace(n_cells=1000)
+            self.prob = types.SimpleNamespace(_dir_rows=list(range(30)), N=5000)
+            self.variant, self.n_dofs, self.dt = bench.WORKLOADS[workload][0], 5000, 2e-4
+            self.ilu_ordering, self.ilu_ordering_schur, self.n = 2, 1, 0
+
+        def step(self):
+            self.n += 1
+            if fail_at is not None and self.n == fail_at:
+                raise RuntimeError("SolverControl::NoConvergence: inner GMRES")
+            dt = step_s * (20.0 if slow_after is not None and self.n > slow_after else 1.0)
+            _time.sleep(dt)
+            self.e.dev_ms += 1e3 * dt
+            return 40 + self.n
+
+        def prepare(self):
+            return [self.step(), self.step()]
+
+    return FakeRun
+
+
+def _run_gpu_arm(monkeypatch, capsys, argv, step_s=0.01, fail_at=None, budget=None, slow_after=None):
+    import importlib
+    import types
+
+    import torch
+
+    sys.path.insert(0, ROOT)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    if budget is not None:
+        monkeypatch.setenv("NSB_BENCH_BUDGET_S", str(budget))
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(bench, "GpuRun", _fake_gpurun(bench, step_s, fail_at, slow_after))
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+    monkeypatch.setattr(bench, "ClockSampler", lambda *_: types.SimpleNamespace(
+        start=lambda: None, stop=lambda: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}))
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    bench.main()
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    return bench, json.loads(lines[0])
+
+
+def test_gpu_arm_prints_the_contract_line(monkeypatch, capsys):
+    bench, d = _run_gpu_arm(monkeypatch, capsys, ["--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "roofline", "clocks", "gpu_launches"):
+        assert key in d, key
+    assert d["steps"] == 4 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["gpu_launches"] == 1234
+    assert d["detail"]["truncated"] is False and d["detail"]["failure"] is None
+    assert d["value"] == pytest.approx(5000 * 4 / (d["ms_per_step"] * 4e-3)) and d["e2e"]["value"] <= d["value"] * 1.001
+    assert d["e2e"]["h2d_bytes_per_step"] == 30 * 8 and d["e2e"]["d2h_bytes_per_step"] == 5000 * 8
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and "spmv_S" not in r["kernels"]
+    assert d["detail"]["same_mesh"]["steps"] == 5  # the like-for-like leg on the mesh of the CPU arm
+
+
+def test_gpu_arm_times_fewer_steps_when_the_budget_runs_out(monkeypatch, capsys):
+    """20 steps of 0.4 s do not fit what a 4 s budget leaves: fewer steps are timed and the line says so."""
+    _, d = _run_gpu_arm(monkeypatch, capsys, ["--steps", "20", "--warmup", "1", "--no-cpu-baseline"], step_s=0.4, budget=29.0)
+    assert 1 <= d["steps"] < 20 and d["detail"]["truncated"] is True and d["detail"]["steps_requested"] == 20
+    assert len(d["detail"]["outer_iterations"]) == d["steps"]
+
+
+def test_gpu_arm_stops_inside_the_timed_loop_when_steps_turn_out_slower(monkeypatch, capsys):
+    """The warm-up estimate (0.05 s per step) lets all 6 steps through, but the timed steps cost 1 s each: the guard
+    inside the loop ends the measurement instead of overrunning the budget."""
+    _, d = _run_gpu_arm(monkeypatch, capsys, ["--steps", "6", "--warmup", "1", "--no-cpu-baseline"], step_s=0.05, budget=47.0,
+                        slow_after=3)
+    assert 1 <= d["steps"] < 6 and d["detail"]["truncated"] is True and d["detail"]["failure"] is None
+    assert d["ms_per_step"] == pytest.approx(1000.0, rel=0.05)
+
+
+def test_gpu_arm_keeps_the_finished_steps_when_a_step_raises(monkeypatch, capsys):
+    # 2 start-up + 1 warm-up steps, then the 3rd timed step (6th call) raises
+    _, d = _run_gpu_arm(monkeypatch, capsys, ["--steps", "5", "--warmup", "1", "--no-cpu-baseline"], fail_at=6)
+    assert d["steps"] == 2 and d["detail"]["truncated"] is True and "NoConvergence" in d["detail"]["failure"]
+    assert len(d["detail"]["outer_iterations"]) == 2 and d["value"] > 0
