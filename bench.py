@@ -302,8 +302,14 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     budget = float(os.environ.get("NSB_BENCH_BUDGET_S", "780"))
+    # NSB_BENCH_BACKEND=gloo exists for the CPU test of this function's multi-rank control flow (tests/test_bench_contract.py,
+    # fake engines); a real run is always NCCL
+    backend = os.environ.get("NSB_BENCH_BACKEND", "nccl")
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
     torch.cuda.set_device(local_rank)
     log(f"process group up: world {world}, OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')}")
 
@@ -315,7 +321,7 @@ def run_gpu(args):
     def reduce(x, op="max"):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device="cuda" if backend == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
         return float(t.item())
 

@@ -152,3 +152,21 @@ def test_gpu_arm_keeps_the_finished_steps_when_a_step_raises(monkeypatch, capsys
     _, d = _run_gpu_arm(monkeypatch, capsys, ["--steps", "5", "--warmup", "1", "--no-cpu-baseline"], fail_at=6)
     assert d["steps"] == 2 and d["detail"]["truncated"] is True and "NoConvergence" in d["detail"]["failure"]
     assert len(d["detail"]["outer_iterations"]) == 2 and d["value"] > 0
+
+
+def test_gpu_arm_on_two_ranks_over_gloo():
+    """world_size 2: one line from rank 0, times are the max over ranks (rank 1 is twice as slow), both ranks stop at
+    the same step when the budget guard trips."""
+    env = dict(os.environ, NSB_BENCH_BUDGET_S="27.5", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29653", os.path.join(ROOT, "tests", "_bench_fake_rank.py"), "--gpus", "2",
+                        "--steps", "6", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["transport"] == "p2p" and "cpu_baseline" not in d
+    assert 1 <= d["steps"] < 6 and d["detail"]["truncated"] is True  # extras 25 s + 0.8 s per slow step against 27.5 s
+    assert d["ms_per_step"] == pytest.approx(800.0, rel=0.1)         # rank 1's time, not rank 0's 400 ms
