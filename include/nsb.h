@@ -249,6 +249,15 @@ int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, 
                        const int32_t *leaf_levels, int32_t min_active, int32_t bs, double *rel_err, int32_t *stats,
                        int32_t *order_out);
 
+/* CPU-only self check of the block multicolour ILU storage (ilu_ordering = 2): the ordering of an n x n pattern (blocks
+ * of one colour independent), then both factors packed as for the device and walked by a host emulation of the sweep
+ * kernel (four passes of eight rows over the entries leaving a block, staged-list indices below xcap, sequential
+ * elimination inside the block) with a pseudo-random factor and bs right-hand sides; *rel_err = largest difference to
+ * plain forward / backward substitution (>= 1e30: structural violation).  stats[4]: blocks, colours, max outside rows
+ * and max in-block entries per block.  order_out[n] (may be NULL): factor row -> row.  Test infrastructure. */
+int nsb_debug_bsell_check(int32_t n, const int32_t *rowptr, const int32_t *colind, int32_t bs, int32_t xcap, double *rel_err,
+                          int32_t *stats, int32_t *order_out);
+
 /* CPU-only fingerprint of the HOST side of nsb_set_mesh + nsb_finalize_setup (sparsity patterns, scatter map, SpMV
  * formats, ILU orderings and their packed storage): the same code runs on a handle without device state and every
  * array setup would upload is hashed (FNV-1a, upload order) into hashes[cap]; *n_hashes = number of uploads.  Pins the

@@ -1012,6 +1012,28 @@ double sd_debug_check(const Csr &A, const double *xyz, int gdim, const int *leaf
                        o.level_part_ptr, bs, stats);
 }
 
+// CPU-only check of the block multicolour ordering and its packed storage (tests/test_host_cpu.py)
+double bsell_host_check(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                        const std::vector<int> &blk_ptr, const std::vector<int> &colour_blk, int bs, int xcap, int *stats);
+double bsell_debug_check(const Csr &A, int bs, int xcap, int *stats, int *order_out)
+{
+  std::vector<int> order, colour_ptr, blk_ptr, colour_blk;
+  block_multicolour_order(A.n_rows, A, A.n_rows, order, colour_ptr, blk_ptr, colour_blk);
+  std::vector<int> rowptr, colind, src, diagpos;
+  permute_pattern(A, order, A.n_rows, rowptr, colind, src, diagpos);
+  // blocks of one colour must not touch, and a row may only couple with rows of other colours or of its own block
+  std::vector<int> blk_of(A.n_rows), col_of_blk(blk_ptr.size() - 1);
+  for (size_t c = 0; c + 1 < colour_blk.size(); ++c)
+    for (int b = colour_blk[c]; b < colour_blk[c + 1]; ++b) col_of_blk[b] = int(c);
+  for (size_t b = 0; b + 1 < blk_ptr.size(); ++b)
+    for (int r = blk_ptr[b]; r < blk_ptr[b + 1]; ++r) blk_of[r] = int(b);
+  for (int r = 0; r < A.n_rows; ++r)
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
+      if (blk_of[colind[e]] != blk_of[r] && col_of_blk[blk_of[colind[e]]] == col_of_blk[blk_of[r]]) return 1.5e30;
+  if (order_out) std::copy(order.begin(), order.end(), order_out);
+  return bsell_host_check(rowptr, colind, diagpos, blk_ptr, colour_blk, bs, xcap, stats);
+}
+
 static std::vector<int> sd_leaf_rows(int bs_rhs)
 { // rows per part and level: a part's rows + ring times bs_rhs doubles should leave room for two CTAs per SM.
   // NSB_SD_LEAF = "l1[,l2[,l3]]" overrides (one entry = one level).

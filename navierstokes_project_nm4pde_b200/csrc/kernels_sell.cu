@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <numeric>
 
+#include <cmath>
 #include <memory>
 
 #include "nsb_internal.hpp"
@@ -718,9 +719,17 @@ void append_chunks(RawArray<T> &dst, const std::vector<BsellChunk> &chunks, std:
 }
 } // namespace
 
+// host copies of one factor's block storage for the CPU emulation of the sweeps (bsell_host_check, test only)
+struct BsellHost {
+  std::vector<int> e_ptr, i_ptr, x_ptr, e_map, e_gcol, i_map, x_ids;
+  std::vector<unsigned short> e_lix, i_off;
+  std::vector<unsigned char> e_prow, i_col;
+  std::vector<unsigned> e_len;
+};
+
 static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<int> &colind,
                             const std::vector<int> &diagpos, const std::vector<int> &blk_ptr,
-                            const std::vector<int> &colour_blk, bool lower, DevBsell &out)
+                            const std::vector<int> &colour_blk, bool lower, DevBsell &out, BsellHost *keep = nullptr)
 {
   const int nb = int(blk_ptr.size()) - 1;
   std::vector<unsigned> e_len(nb, 0u), i_mask(nb, 0u); // i_mask: local rows that occur as an intra-block column
@@ -873,7 +882,133 @@ static void bsell_build_one(const std::vector<int> &rowptr, const std::vector<in
   out.i_ptr.upload(i_ptr); out.i_map.upload(i_map.p.get(), i_map.n); out.i_off.upload(i_off); out.i_col.upload(i_col.p.get(), i_col.n);
   out.i_mask.upload(i_mask);
   out.i_val.alloc(i_col.size());
+  if (keep) {
+    keep->e_ptr = e_ptr; keep->i_ptr = i_ptr; keep->x_ptr = x_ptr; keep->e_len = e_len; keep->e_prow = e_prow; keep->i_off = i_off;
+    keep->e_map.assign(e_map.p.get(), e_map.p.get() + e_map.n);
+    keep->e_gcol.assign(e_gcol.p.get(), e_gcol.p.get() + e_gcol.n);
+    keep->i_map.assign(i_map.p.get(), i_map.p.get() + i_map.n);
+    keep->x_ids.assign(x_ids.p.get(), x_ids.p.get() + x_ids.n);
+    keep->e_lix.assign(e_col.p.get(), e_col.p.get() + e_col.n);
+    keep->i_col.assign(i_col.p.get(), i_col.p.get() + i_col.n);
+  }
 }
+
+// ---- CPU emulation of k_bsell on the packed storage (nsb_debug_bsell_check, tests/test_host_cpu.py) ---------------
+// Builds the block storage of both factors exactly as bsell_build does (the uploads are skipped: setup dry run), fills
+// it with a pseudo-random factor and walks it the way the kernel does -- per block: the four passes of eight rows with
+// four lanes per row over the entries that leave the block (staged list index below `xcap`, factor row otherwise),
+// (pass, slot) -> local row through e_prow, then the sequential elimination over the in-block entries -- colour by
+// colour, the blocks of a colour in REVERSE order (they must be independent).  Returns the largest difference to plain
+// forward / backward substitution on the permuted CSR pattern, relative to the largest entry; 1e30 and above name a
+// structural violation.  stats[4]: blocks, colours, max outside rows per block, max in-block entries per block.
+double bsell_host_check(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                        const std::vector<int> &blk_ptr, const std::vector<int> &colour_blk, int bs, int xcap, int *stats)
+{
+  const int n = int(rowptr.size()) - 1, nb = int(blk_ptr.size()) - 1, ncol = int(colour_blk.size()) - 1;
+  DevBsell dL, dU;
+  BsellHost hL, hU;
+  const bool was_on = g_dry.on;
+  g_dry.on = true; // no device: the uploads inside bsell_build_one are recorded, not copied
+  try {
+    bsell_build_one(rowptr, colind, diagpos, blk_ptr, colour_blk, true, dL, &hL);
+    bsell_build_one(rowptr, colind, diagpos, blk_ptr, colour_blk, false, dU, &hU);
+  } catch (...) { g_dry.on = was_on; throw; }
+  g_dry.on = was_on;
+  if (!was_on) g_dry.log.clear();
+  if (stats) { stats[0] = nb; stats[1] = ncol; stats[2] = std::max(dL.max_nx, dU.max_nx); stats[3] = std::max(dL.max_int, dU.max_int); }
+  // pseudo-random factor: small off-diagonal entries (a well-conditioned solve), inverse diagonal in [0.5, 1.5]
+  auto rnd = [](uint64_t k) { k = (k + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull; k ^= k >> 31; k *= 0x94D049BB133111EBull; k ^= k >> 29;
+                              return double(k >> 11) / double(1ull << 53); };
+  std::vector<double> val(colind.size()), dinv(n), x(size_t(n) * bs);
+  for (int k = 0; k < n; ++k) {
+    const int len = std::max(1, rowptr[k + 1] - rowptr[k]);
+    for (int e = rowptr[k]; e < rowptr[k + 1]; ++e) val[e] = (rnd(uint64_t(e)) - 0.5) / len;
+    dinv[k] = 0.5 + rnd(uint64_t(k) + (1ull << 40));
+    for (int d = 0; d < bs; ++d) x[size_t(k) * bs + d] = rnd(uint64_t(k) * 3 + d + (1ull << 41)) - 0.5;
+  }
+  // reference: y = U^-1 D^-1 L^-1 x with Ifpack's scaling (kernels_linalg.cu, k_ilu_factor_level)
+  std::vector<double> ref(x);
+  for (int k = 0; k < n; ++k)
+    for (int e = rowptr[k]; e < diagpos[k]; ++e)
+      for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] -= val[e] * ref[size_t(colind[e]) * bs + d];
+  for (int k = n - 1; k >= 0; --k) {
+    for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] *= dinv[k];
+    for (int e = diagpos[k] + 1; e < rowptr[k + 1]; ++e)
+      for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] -= val[e] * ref[size_t(colind[e]) * bs + d];
+  }
+  // emulation
+  std::vector<double> y(x);
+  const double nan = std::nan("");
+  for (int dir = 0; dir < 2; ++dir) {
+    const BsellHost &B = dir == 0 ? hL : hU;
+    const DevBsell &D = dir == 0 ? dL : dU;
+    std::vector<double> e_val(B.e_map.size()), i_val(B.i_map.size());
+    for (size_t o = 0; o < e_val.size(); ++o) e_val[o] = B.e_map[o] >= 0 ? val[B.e_map[o]] : 0.0; // k_sell_fill
+    for (size_t o = 0; o < i_val.size(); ++o) i_val[o] = val[B.i_map[o]];
+    for (int cc = 0; cc < ncol; ++cc) {
+      const int c = dir == 0 ? cc : ncol - 1 - cc;
+      const int cap = std::min(xcap, D.col_max_nx[c]); // rows of the staged list beyond the capacity come from e_col
+      for (int b = colour_blk[c + 1] - 1; b >= colour_blk[c]; --b) {
+        const int r0 = blk_ptr[b], nr = blk_ptr[b + 1] - r0;
+        if (nr < 1 || nr > 32) return 1e30;
+        double res[32][3] = {}, acc[32][3];
+        for (int l = 0; l < 32; ++l)
+          for (int d = 0; d < bs; ++d) {
+            acc[l][d] = nan;
+            if (l < nr) res[l][d] = dir == 0 ? y[size_t(r0 + l) * bs + d] : y[size_t(r0 + l) * bs + d] * dinv[r0 + l];
+          }
+        size_t pos = size_t(B.e_ptr[b]);
+        if (pos % 32) return 2e30;
+        const unsigned lens = B.e_len[b];
+        for (int q = 0; q < 4; ++q) {
+          const int len = int((lens >> (8 * q)) & 255u);
+          double a[8][3] = {};
+          for (int k = 0; k < len; ++k)
+            for (int l = 0; l < 32; ++l) {
+              const size_t o = pos + size_t(k) * 32 + l;
+              const int li = int(B.e_lix[o]);
+              if (B.e_map[o] >= 0 && (li >= B.x_ptr[b + 1] - B.x_ptr[b] || B.x_ids[B.x_ptr[b] + li] != B.e_gcol[o])) return 3e30;
+              const int col = li < cap ? B.x_ids[B.x_ptr[b] + li] : B.e_gcol[o];
+              if (col >= r0 && col < r0 + nr) return 4e30; // an outside entry must leave the block
+              for (int d = 0; d < bs; ++d) a[l / 4][d] += e_val[o] * y[size_t(col) * bs + d];
+            }
+          pos += size_t(len) * 32;
+          for (int slot = 0; slot < 8; ++slot) {
+            const int lr = int(B.e_prow[size_t(b) * 32 + q * 8 + slot]);
+            if (lr > 31 || !std::isnan(acc[lr][0])) return 5e30; // every local row sits in exactly one (pass, slot)
+            for (int d = 0; d < bs; ++d) acc[lr][d] = a[slot][d];
+          }
+        }
+        if (pos != size_t(B.e_ptr[b + 1])) return 6e30;
+        for (int l = 0; l < 32; ++l)
+          for (int d = 0; d < bs; ++d) res[l][d] -= acc[l][d];
+        // in-block entries: sequential elimination, one cursor per local row
+        const int ib = B.i_ptr[b];
+        int p[32], pe[32];
+        for (int l = 0; l < 32; ++l) { p[l] = l < nr ? int(B.i_off[size_t(b) * 33 + l]) : 0; pe[l] = l < nr ? int(B.i_off[size_t(b) * 33 + l + 1]) : 0; }
+        for (int step = 0; step < 32; ++step) {
+          const int r = dir == 0 ? step : 31 - step;
+          if (r >= nr) continue;
+          for (int l = 0; l < nr; ++l)
+            if (p[l] < pe[l] && int(B.i_col[ib + p[l]]) == r) {
+              if ((dir == 0 && r >= l) || (dir == 1 && r <= l)) return 7e30; // L: earlier rows only, U: later rows only
+              for (int d = 0; d < bs; ++d) res[l][d] -= i_val[ib + p[l]] * res[r][d];
+              ++p[l];
+            }
+        }
+        for (int l = 0; l < nr; ++l)
+          if (p[l] != pe[l]) return 8e30; // an in-block entry the sweep never reaches
+        if (ib + int(B.i_off[size_t(b) * 33 + 32]) != B.i_ptr[b + 1]) return 9e30;
+        for (int l = 0; l < nr; ++l)
+          for (int d = 0; d < bs; ++d) y[size_t(r0 + l) * bs + d] = res[l][d];
+      }
+    }
+  }
+  double err = 0, scale = 0;
+  for (size_t k = 0; k < y.size(); ++k) { err = std::max(err, std::fabs(y[k] - ref[k])); scale = std::max(scale, std::fabs(ref[k])); }
+  return err / std::max(scale, 1e-300);
+}
+
 
 void bsell_build(DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
                  const std::vector<int> &diagpos, const std::vector<int> &blk_ptr, const std::vector<int> &colour_blk)

@@ -303,6 +303,51 @@ def test_subdomain_ilu_storage_cpu(gen, dim, bs, leaf):
         assert stats[6] == (1 if levels[1] == 0 else 3) or stats[1] == n
 
 
+def _graph_of(gen, dim, bs):
+    """Node graph of F_s (bs = dim) or the two-ring pressure graph of B D^-1 B^T (bs = 1) of a generated mesh."""
+    import scipy.sparse as sp
+
+    d = HostDofs(gen())
+    cd = d.cell_dofs(copy=False)
+    nv = dim + 1
+    if bs == 1:
+        ids, n = cd[:, [v * (dim + 1) + dim for v in range(nv)]] - d.n_u, d.n_p
+    else:
+        ne = 3 if dim == 2 else 6
+        cols = [v * (dim + 1) for v in range(nv)] + [nv * (dim + 1) + e * dim for e in range(ne)]
+        ids, n = cd[:, cols] // dim, d.n_nodes
+    k = ids.shape[1]
+    A = sp.csr_matrix((np.ones(ids.size * k), (np.repeat(ids, k, axis=1).ravel(), np.tile(ids, (1, k)).ravel())), shape=(n, n))
+    if bs == 1:
+        A = (A @ A).tocsr()
+    A.sum_duplicates(); A.sort_indices()
+    return n, A.indptr.astype(np.int32), A.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize("gen,dim,bs", [(lambda: HostMesh.cylinder3d(1, 3), 3, 3), (lambda: HostMesh.cylinder2d(2), 2, 2),
+                                        (lambda: HostMesh.cylinder3d(1, 3), 3, 1), (lambda: HostMesh.cube(4), 3, 3),
+                                        (lambda: HostMesh.cylinder3d(2, 8), 3, 3)])
+def test_block_multicolour_ilu_storage_cpu(gen, dim, bs):
+    """ilu_ordering = 2 without a GPU (nsb_debug_bsell_check): the block multicolour ordering is a permutation whose
+    blocks of one colour do not touch, and the packed block storage of both factors (passes of eight rows, staged-list
+    indices, (pass, slot) -> row table, in-block cursors) reproduces plain forward / backward substitution through a
+    host emulation of the sweep kernel -- with the whole outside list staged, with a capacity of 8 rows (the rest
+    gathered by factor row, as the kernel does beyond NSB_BSELL_XCAP) and without staging (velocity block)."""
+    import ctypes as C
+
+    from navierstokes_project_nm4pde_b200 import _lib
+    from navierstokes_project_nm4pde_b200._lib import iptr
+
+    n, rp, ci = _graph_of(gen, dim, bs)
+    err, stats, order = C.c_double(0), np.zeros(4, np.int32), np.zeros(n, np.int32)
+    for xcap in (65535, 8, 0):
+        rc = _lib.lib().nsb_debug_bsell_check(n, iptr(rp), iptr(ci), bs, xcap, C.byref(err), iptr(stats), iptr(order))
+        assert rc == 0
+        assert sorted(order.tolist()) == list(range(n))
+        assert err.value < 1e-12, err.value
+        assert stats[0] == (n + 31) // 32 and 2 <= stats[1] <= 64 and 0 < stats[2] <= 65535 and stats[3] > 0
+
+
 def test_driver_rendezvous_without_gpu(tmp_path):
     """The launcher contract of the C++ drivers (csrc/host/rendezvous.hpp, scripts/nsb_launch.sh): three
     processes find each other over TCP and all-gather blobs of 1 B .. 100 kB; no GPU is touched."""
