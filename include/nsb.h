@@ -258,6 +258,16 @@ int nsb_debug_sd_check(int32_t n, const int32_t *rowptr, const int32_t *colind, 
 int nsb_debug_bsell_check(int32_t n, const int32_t *rowptr, const int32_t *colind, int32_t bs, int32_t xcap, double *rel_err,
                           int32_t *stats, int32_t *order_out);
 
+/* CPU-only self check of the point multicolour ILU storage (ilu_ordering = 1) and of the SELL-32 SpMV format: greedy
+ * colouring of an n x n pattern (colours are independent sets), the strictly lower / upper factor parts in SELL-32 with
+ * the colours as row ranges (`lanes` = 1 | 4 lanes per row, rows length-sorted inside windows of `window` rows), and the
+ * whole pattern in SELL-32; a host emulation of the sweep / SpMV kernel (one warp per slice, partial sums of the lanes of
+ * a row combined, slices of a colour in reverse order) with a pseudo-random factor and bs right-hand sides; *rel_err =
+ * largest difference to plain substitution and to a CSR product (>= 1e30: structural violation).  stats[3]: colours,
+ * slices of L, padded slots per stored entry of L in per mille.  Test infrastructure. */
+int nsb_debug_sell_check(int32_t n, const int32_t *rowptr, const int32_t *colind, int32_t bs, int32_t lanes, int32_t window,
+                         double *rel_err, int32_t *stats, int32_t *order_out);
+
 /* CPU-only fingerprint of the HOST side of nsb_set_mesh + nsb_finalize_setup (sparsity patterns, scatter map, SpMV
  * formats, ILU orderings and their packed storage): the same code runs on a handle without device state and every
  * array setup would upload is hashed (FNV-1a, upload order) into hashes[cap]; *n_hashes = number of uploads.  Pins the

@@ -73,6 +73,7 @@ SIGNATURES = {
     "nsb_debug_sd_check": (C.c_int, [C.c_int32, c_int_p, c_int_p, c_double_p, C.c_int32, c_int_p, C.c_int32, C.c_int32,
                                      c_double_p, c_int_p, c_int_p]),
     "nsb_debug_bsell_check": (C.c_int, [C.c_int32, c_int_p, c_int_p, C.c_int32, C.c_int32, c_double_p, c_int_p, c_int_p]),
+    "nsb_debug_sell_check": (C.c_int, [C.c_int32, c_int_p, c_int_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_int_p, c_int_p]),
     "nsb_debug_setup_fingerprint": (C.c_int, [C.c_int32, C.c_int32, c_double_p, c_int_p, C.c_int32, C.c_int32, C.c_int32,
                                               C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, c_int_p]),
     # host prerequisites

@@ -1034,6 +1034,24 @@ double bsell_debug_check(const Csr &A, int bs, int xcap, int *stats, int *order_
   return bsell_host_check(rowptr, colind, diagpos, blk_ptr, colour_blk, bs, xcap, stats);
 }
 
+// CPU-only check of the point multicolour ordering and the SELL-32 storage of its factors (tests/test_host_cpu.py)
+double sell_host_check(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                       const std::vector<int> &colour_ptr, int bs, int lanes, int window, int *stats);
+double sell_debug_check(const Csr &A, int bs, int lanes, int window, int *stats, int *order_out)
+{
+  std::vector<int> order, colour_ptr;
+  multicolour_order(A.n_rows, A, A.n_rows, 0, order, colour_ptr);
+  std::vector<int> rowptr, colind, src, diagpos;
+  permute_pattern(A, order, A.n_rows, rowptr, colind, src, diagpos);
+  // a colour is an independent set: a row only couples with itself inside its colour
+  for (size_t c = 0; c + 1 < colour_ptr.size(); ++c)
+    for (int r = colour_ptr[c]; r < colour_ptr[c + 1]; ++r)
+      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
+        if (colind[e] != r && colind[e] >= colour_ptr[c] && colind[e] < colour_ptr[c + 1]) return 1.5e30;
+  if (order_out) std::copy(order.begin(), order.end(), order_out);
+  return sell_host_check(rowptr, colind, diagpos, colour_ptr, bs, lanes, window, stats);
+}
+
 static std::vector<int> sd_leaf_rows(int bs_rhs)
 { // rows per part and level: a part's rows + ring times bs_rhs doubles should leave room for two CTAs per SM.
   // NSB_SD_LEAF = "l1[,l2[,l3]]" overrides (one entry = one level).

@@ -170,6 +170,13 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
 void sell_build(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges, int window,
                 int lanes, DevSell &out)
 {
+  sell_build_keep(rowptr, colind, src, ranges, window, lanes, out, nullptr);
+}
+
+// keep (test only, sell_host_check): host copies of the packed arrays
+void sell_build_keep(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges,
+                     int window, int lanes, DevSell &out, SellHost *keep)
+{
   out.range_slice.assign(ranges.size(), 0);
   out.lanes = lanes;
   const int R = 32 / lanes; // rows per slice
@@ -246,6 +253,122 @@ void sell_build(const std::vector<int> &rowptr, const int *colind, const int *sr
   out.col.upload(col.get(), n_slots);
   out.map.upload(map.get(), n_slots);
   out.val.alloc(n_slots);
+  if (keep) {
+    keep->slice_ptr = slice_ptr;
+    keep->rowid.assign(rowid.get(), rowid.get() + size_t(nsl) * 32);
+    keep->col.assign(col.get(), col.get() + n_slots);
+    keep->map.assign(map.get(), map.get() + n_slots);
+  }
+}
+
+// ---- CPU emulation of k_sell3 on the packed storage (nsb_debug_sell_check, tests/test_host_cpu.py) ----------------
+// SELL-32 copies of the split L / U factors with the colours as row ranges, and of the whole matrix for the SpMV,
+// built exactly as for the device (uploads skipped: setup dry run), filled with a pseudo-random factor and walked the
+// way the kernel does: one warp per slice, lane l owns row rowid[32 s + l] (LPR lanes per row, partial sums added),
+// `len` steps of 32 slots; colours forward for L, backward for U, the slices of a colour in REVERSE order.  Returns
+// the largest difference to plain substitution / CSR SpMV relative to the largest entry (>= 1e30: structural
+// violation).  stats[3]: colours, slices of L, padded slots of L per stored entry in per mille.
+double sell_host_check(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+                       const std::vector<int> &colour_ptr, int bs, int lanes, int window, int *stats)
+{
+  const int n = int(rowptr.size()) - 1, ncol = int(colour_ptr.size()) - 1;
+  std::vector<int> Lp, Up;
+  std::unique_ptr<int[]> Lc, mapL, Uc, mapU;
+  split_lu(rowptr, colind, diagpos, Lp, Lc, mapL, Up, Uc, mapU);
+  DevSell dL, dU, dA;
+  SellHost hL, hU, hA;
+  const bool was_on = g_dry.on;
+  g_dry.on = true;
+  try {
+    sell_build_keep(Lp, Lc.get(), mapL.get(), colour_ptr, window, lanes, dL, &hL);
+    sell_build_keep(Up, Uc.get(), mapU.get(), colour_ptr, window, lanes, dU, &hU);
+    sell_build_keep(rowptr, colind.data(), nullptr, {0, n}, 2048, lanes, dA, &hA);
+  } catch (...) { g_dry.on = was_on; throw; }
+  g_dry.on = was_on;
+  if (!was_on) g_dry.log.clear();
+  if (stats) { stats[0] = ncol; stats[1] = dL.n_slices; stats[2] = Lp[n] ? int(1000.0 * double(dL.n_slots) / Lp[n]) : 0; }
+  auto rnd = [](uint64_t k) { k = (k + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull; k ^= k >> 31; k *= 0x94D049BB133111EBull; k ^= k >> 29;
+                              return double(k >> 11) / double(1ull << 53); };
+  std::vector<double> val(colind.size()), dinv(n), x(size_t(n) * bs);
+  for (int k = 0; k < n; ++k) {
+    const int len = std::max(1, rowptr[k + 1] - rowptr[k]);
+    for (int e = rowptr[k]; e < rowptr[k + 1]; ++e) val[e] = (rnd(uint64_t(e)) - 0.5) / len;
+    dinv[k] = 0.5 + rnd(uint64_t(k) + (1ull << 40));
+    for (int d = 0; d < bs; ++d) x[size_t(k) * bs + d] = rnd(uint64_t(k) * 3 + d + (1ull << 41)) - 0.5;
+  }
+  std::vector<double> ref(x), ref_mv(size_t(n) * bs, 0.0);
+  for (int k = 0; k < n; ++k)
+    for (int e = rowptr[k]; e < rowptr[k + 1]; ++e)
+      for (int d = 0; d < bs; ++d) ref_mv[size_t(k) * bs + d] += val[e] * x[size_t(colind[e]) * bs + d];
+  for (int k = 0; k < n; ++k)
+    for (int e = rowptr[k]; e < diagpos[k]; ++e)
+      for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] -= val[e] * ref[size_t(colind[e]) * bs + d];
+  for (int k = n - 1; k >= 0; --k) {
+    for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] *= dinv[k];
+    for (int e = diagpos[k] + 1; e < rowptr[k + 1]; ++e)
+      for (int d = 0; d < bs; ++d) ref[size_t(k) * bs + d] -= val[e] * ref[size_t(colind[e]) * bs + d];
+  }
+  // one slice as the kernel walks it: sums[l] = partial sum of lane l, combined over the `lanes` lanes of a row
+  auto slice_sums = [&](const SellHost &S, int s, const std::vector<double> &v, const std::vector<double> &src_vec,
+                        double (&sum)[32][3], std::vector<char> &seen) -> double {
+    const int base = S.slice_ptr[s], len = (S.slice_ptr[s + 1] - base) >> 5;
+    if (base % 32 || (S.slice_ptr[s + 1] - base) % 32) return 1e30;
+    for (int l = 0; l < 32; ++l) {
+      const int r = S.rowid[size_t(s) * 32 + l];
+      if (r >= n || (l % lanes && r != S.rowid[size_t(s) * 32 + l - 1])) return 2e30; // the lanes of a row are adjacent
+      if (r >= 0 && l % lanes == 0) { if (seen[r]) return 3e30; seen[r] = 1; }         // every row in exactly one slice
+      for (int d = 0; d < bs; ++d) sum[l][d] = 0.0;
+      for (int k = 0; k < len; ++k) {
+        const size_t o = size_t(base) + size_t(k) * 32 + l;
+        const double a = S.map[o] >= 0 ? v[S.map[o]] : 0.0; // k_sell_fill
+        if (S.col[o] < 0 || S.col[o] >= n) return 4e30;      // padding names a valid row (value 0)
+        for (int d = 0; d < bs; ++d) sum[l][d] += a * src_vec[size_t(S.col[o]) * bs + d];
+      }
+    }
+    for (int l = 0; l < 32; l += lanes)
+      for (int j = 1; j < lanes; ++j)
+        for (int d = 0; d < bs; ++d) sum[l][d] += sum[l + j][d];
+    return 0.0;
+  };
+  double sum[32][3];
+  std::vector<char> seen(n, 0);
+  // SpMV
+  std::vector<double> y_mv(size_t(n) * bs, 0.0);
+  for (int s = 0; s < dA.n_slices; ++s) {
+    const double bad = slice_sums(hA, s, val, x, sum, seen);
+    if (bad > 0) return bad;
+    for (int l = 0; l < 32; l += lanes) {
+      const int r = hA.rowid[size_t(s) * 32 + l];
+      if (r >= 0) for (int d = 0; d < bs; ++d) y_mv[size_t(r) * bs + d] = sum[l][d];
+    }
+  }
+  for (int k = 0; k < n; ++k) if (!seen[k]) return 5e30;
+  // triangular sweeps
+  std::vector<double> y(x);
+  for (int dir = 0; dir < 2; ++dir) {
+    const SellHost &S = dir == 0 ? hL : hU;
+    const DevSell &D = dir == 0 ? dL : dU;
+    std::fill(seen.begin(), seen.end(), 0);
+    for (int cc = 0; cc < ncol; ++cc) {
+      const int c = dir == 0 ? cc : ncol - 1 - cc;
+      for (int s = D.range_slice[c + 1] - 1; s >= D.range_slice[c]; --s) {
+        const double bad = slice_sums(S, s, val, y, sum, seen);
+        if (bad > 0) return bad + 10e30;
+        for (int l = 0; l < 32; l += lanes) {
+          const int r = S.rowid[size_t(s) * 32 + l];
+          if (r < 0) continue;
+          if (r < colour_ptr[c] || r >= colour_ptr[c + 1]) return 6e30; // a slice never mixes colours
+          for (int d = 0; d < bs; ++d)
+            y[size_t(r) * bs + d] = dir == 0 ? y[size_t(r) * bs + d] - sum[l][d] : y[size_t(r) * bs + d] * dinv[r] - sum[l][d];
+        }
+      }
+    }
+    for (int k = 0; k < n; ++k) if (!seen[k]) return 7e30;
+  }
+  double err = 0, scale = 0;
+  for (size_t k = 0; k < y.size(); ++k) { err = std::max(err, std::fabs(y[k] - ref[k])); scale = std::max(scale, std::fabs(ref[k])); }
+  for (size_t k = 0; k < y.size(); ++k) { err = std::max(err, std::fabs(y_mv[k] - ref_mv[k])); scale = std::max(scale, std::fabs(ref_mv[k])); }
+  return err / std::max(scale, 1e-300);
 }
 
 void sell_fill(Handle &H, DevSell &S, const double *src)

@@ -229,20 +229,22 @@ void stream_spmv_S(Handle &H, const double *x_p, int goff_p, double *y_p)
   H.launches++;
 }
 
-// ---- colour-scheduled triangular solves on split L / U factors --------------------------------
-// h_rowptr / h_colind: the combined factor pattern in the permuted index space (diag inside).
-void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
-                      const std::vector<int> &diagpos, const std::vector<int> &colour_ptr)
+// strictly lower / strictly upper parts of a factor pattern (diagonal inside) as two CSR structures; map*: position of
+// every entry in the combined pattern
+void split_lu(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+              std::vector<int> &Lp, std::unique_ptr<int[]> &Lc, std::unique_ptr<int[]> &mapL, std::vector<int> &Up,
+              std::unique_ptr<int[]> &Uc, std::unique_ptr<int[]> &mapU)
 {
-  const int n = ilu.n;
-  std::vector<int> Lp(n + 1, 0), Up(n + 1, 0);
+  const int n = int(rowptr.size()) - 1;
+  Lp.assign(n + 1, 0);
+  Up.assign(n + 1, 0);
   for (int k = 0; k < n; ++k) {
     Lp[k + 1] = Lp[k] + (diagpos[k] - rowptr[k]);
     Up[k + 1] = Up[k] + (rowptr[k + 1] - diagpos[k] - 1);
   }
   // uninitialised storage, first touched by the filling threads
   const size_t nL = size_t(Lp[n]), nU = size_t(Up[n]);
-  std::unique_ptr<int[]> Lc(new int[nL + 1]), mapL(new int[nL + 1]), Uc(new int[nU + 1]), mapU(new int[nU + 1]);
+  Lc.reset(new int[nL + 1]); mapL.reset(new int[nL + 1]); Uc.reset(new int[nU + 1]); mapU.reset(new int[nU + 1]);
 #pragma omp parallel for schedule(static)
   for (int k = 0; k < n; ++k) {
     int o = Lp[k];
@@ -250,6 +252,18 @@ void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, co
     o = Up[k];
     for (int e = diagpos[k] + 1; e < rowptr[k + 1]; ++e, ++o) { Uc[o] = colind[e]; mapU[o] = e; }
   }
+}
+
+// ---- colour-scheduled triangular solves on split L / U factors --------------------------------
+// h_rowptr / h_colind: the combined factor pattern in the permuted index space (diag inside).
+void stream_build_ilu(Handle &H, DevIlu &ilu, const std::vector<int> &rowptr, const std::vector<int> &colind,
+                      const std::vector<int> &diagpos, const std::vector<int> &colour_ptr)
+{
+  const int n = ilu.n;
+  std::vector<int> Lp, Up;
+  std::unique_ptr<int[]> Lc, mapL, Uc, mapU;
+  split_lu(rowptr, colind, diagpos, Lp, Lc, mapL, Up, Uc, mapU);
+  const size_t nL = size_t(Lp[n]), nU = size_t(Up[n]);
   ilu.colour_ptr = colour_ptr;
   const int nc = int(colour_ptr.size()) - 1;
   std::vector<int> bL, bU;

@@ -623,6 +623,25 @@ extern "C" int nsb_debug_bsell_check(int32_t n, const int32_t *rowptr, const int
   }
 }
 
+namespace nsb {
+double sell_debug_check(const Csr &A, int bs, int lanes, int window, int *stats, int *order_out);
+}
+extern "C" int nsb_debug_sell_check(int32_t n, const int32_t *rowptr, const int32_t *colind, int32_t bs, int32_t lanes,
+                                    int32_t window, double *rel_err, int32_t *stats, int32_t *order_out)
+{
+  try {
+    if (n <= 0 || !rowptr || !colind || !rel_err || bs < 1 || bs > 3 || (lanes != 1 && lanes != 4) || window < 1) return NSB_ERR_ARG;
+    Csr A;
+    A.n_rows = A.n_cols = n;
+    A.rowptr.assign(rowptr, rowptr + n + 1);
+    A.colind.assign(colind, colind + rowptr[n]);
+    *rel_err = sell_debug_check(A, bs, lanes, window, stats, order_out);
+    return NSB_OK;
+  } catch (const std::exception &) {
+    return NSB_ERR_STATE;
+  }
+}
+
 // ---- CPU-only fingerprint of the host side of setup (no GPU needed; tests/test_setup_fingerprint.py) ------
 // Runs set_mesh_host + finalize_setup on a handle that owns no device state, with the setup dry run on: every array
 // setup would upload is hashed in upload order.  Test infrastructure; computes nothing and is not reachable from the

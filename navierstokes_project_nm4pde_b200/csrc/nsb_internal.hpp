@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -480,6 +481,14 @@ void sell_build(const std::vector<int> &rowptr, const std::vector<int> &colind, 
                 const std::vector<int> &ranges, int window, int lanes, DevSell &out);
 void sell_build(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges, int window,
                 int lanes, DevSell &out);
+// host copies of a SELL-32 structure and the L / U split of a factor pattern (shared by stream_build_ilu and the CPU
+// emulation of the sweeps, sell_host_check)
+struct SellHost { std::vector<int> slice_ptr, rowid, col, map; };
+void sell_build_keep(const std::vector<int> &rowptr, const int *colind, const int *src, const std::vector<int> &ranges,
+                     int window, int lanes, DevSell &out, SellHost *keep);
+void split_lu(const std::vector<int> &rowptr, const std::vector<int> &colind, const std::vector<int> &diagpos,
+              std::vector<int> &Lp, std::unique_ptr<int[]> &Lc, std::unique_ptr<int[]> &mapL, std::vector<int> &Up,
+              std::unique_ptr<int[]> &Uc, std::unique_ptr<int[]> &mapU);
 int sell_lanes_for(int n_rows);
 void sell_fill(Handle &H, DevSell &S, const double *src);
 void sell_spmv_F(Handle &H, const double *x_u, int goff_u, double *y_u);

@@ -348,6 +348,27 @@ def test_block_multicolour_ilu_storage_cpu(gen, dim, bs):
         assert stats[0] == (n + 31) // 32 and 2 <= stats[1] <= 64 and 0 < stats[2] <= 65535 and stats[3] > 0
 
 
+@pytest.mark.parametrize("gen,dim,bs", [(lambda: HostMesh.cylinder3d(1, 3), 3, 3), (lambda: HostMesh.cylinder2d(2), 2, 2),
+                                        (lambda: HostMesh.cylinder3d(1, 3), 3, 1), (lambda: HostMesh.cylinder3d(2, 8), 3, 3)])
+def test_point_multicolour_sell_storage_cpu(gen, dim, bs):
+    """ilu_ordering = 1 and the SpMV format without a GPU (nsb_debug_sell_check): colours are independent sets, and the
+    SELL-32 copies of L, U (colours as row ranges) and of the whole matrix reproduce plain substitution and a CSR
+    product through a host emulation of k_sell3 -- one and four lanes per row, small and large sort windows."""
+    import ctypes as C
+
+    from navierstokes_project_nm4pde_b200 import _lib
+    from navierstokes_project_nm4pde_b200._lib import iptr
+
+    n, rp, ci = _graph_of(gen, dim, bs)
+    err, stats, order = C.c_double(0), np.zeros(3, np.int32), np.zeros(n, np.int32)
+    for lanes, window in ((1, 4096), (4, 4096), (1, 64), (4, 7)):
+        rc = _lib.lib().nsb_debug_sell_check(n, iptr(rp), iptr(ci), bs, lanes, window, C.byref(err), iptr(stats), iptr(order))
+        assert rc == 0
+        assert sorted(order.tolist()) == list(range(n))
+        assert err.value < 1e-12, (lanes, window, err.value)
+        assert 2 <= stats[0] <= 128 and stats[1] >= n * lanes // 32 and 1000 <= stats[2] < 4000
+
+
 def test_driver_rendezvous_without_gpu(tmp_path):
     """The launcher contract of the C++ drivers (csrc/host/rendezvous.hpp, scripts/nsb_launch.sh): three
     processes find each other over TCP and all-gather blobs of 1 B .. 100 kB; no GPU is touched."""
