@@ -136,28 +136,36 @@ void build_rows_chunked(int n_rows, Csr &out, GatherRow &&gather)
 }
 } // namespace
 
-void build_pattern(int64_t nc, const int *cell_rows, int kr, const int *cell_cols, int kc, int n_rows_total,
-                   int n_rows_owned, int n_cols, Csr &out)
+void RowCells::build(int64_t nc, const int *cell_rows, int kr, int n_rows_total)
 {
-  // row -> cells
-  std::vector<int> cnt(size_t(n_rows_total) + 1, 0);
+  ptr.assign(size_t(n_rows_total) + 1, 0);
   for (int64_t c = 0; c < nc; ++c)
-    for (int i = 0; i < kr; ++i) cnt[cell_rows[c * kr + i] + 1]++;
-  for (int r = 0; r < n_rows_total; ++r) cnt[r + 1] += cnt[r];
-  std::vector<int> r2c(cnt[n_rows_total]);
-  {
-    std::vector<int> pos(cnt.begin(), cnt.end() - 1);
-    for (int64_t c = 0; c < nc; ++c)
-      for (int i = 0; i < kr; ++i) r2c[pos[cell_rows[c * kr + i]]++] = int(c);
-  }
+    for (int i = 0; i < kr; ++i) ptr[cell_rows[c * kr + i] + 1]++;
+  for (int r = 0; r < n_rows_total; ++r) ptr[r + 1] += ptr[r];
+  cells.resize(size_t(ptr[n_rows_total]));
+  std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int i = 0; i < kr; ++i) cells[pos[cell_rows[c * kr + i]]++] = int(c);
+}
+
+void build_pattern(const RowCells &rc, const int *cell_cols, int kc, int n_rows_owned, int n_cols, Csr &out)
+{
   out.n_rows = n_rows_owned;
   out.n_cols = n_cols;
   build_rows_chunked(n_rows_owned, out, [&](int r, std::vector<int> &buf) {
-    for (int k = cnt[r]; k < cnt[r + 1]; ++k) {
-      const int *cc = &cell_cols[int64_t(r2c[k]) * kc];
+    for (int k = rc.ptr[r]; k < rc.ptr[r + 1]; ++k) {
+      const int *cc = &cell_cols[int64_t(rc.cells[k]) * kc];
       buf.insert(buf.end(), cc, cc + kc);
     }
   });
+}
+
+void build_pattern(int64_t nc, const int *cell_rows, int kr, const int *cell_cols, int kc, int n_rows_total,
+                   int n_rows_owned, int n_cols, Csr &out)
+{
+  RowCells rc;
+  rc.build(nc, cell_rows, kr, n_rows_total);
+  build_pattern(rc, cell_cols, kc, n_rows_owned, n_cols, out);
 }
 
 void symbolic_product(const Csr &A, const Csr &B, Csr &out)

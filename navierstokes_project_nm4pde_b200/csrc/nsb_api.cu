@@ -320,10 +320,15 @@ static void finalize_setup(Handle &H)
     t_last = now;
   };
   // patterns (DoFTools::make_sparsity_pattern with the coupling table of NavierStokes2D.cpp:109-119)
-  build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_nodes.data(), n2, H.n_nodes, H.n_nodes_owned, H.n_nodes, H.hFs);
-  build_pattern(nc, H.h_cell_nodes.data(), n2, H.h_cell_p.data(), nv1, H.n_nodes, H.n_nodes, H.n_p, H.hBt);
-  build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_nodes.data(), n2, H.n_p, H.n_p_owned, H.n_nodes, H.hB);
-  build_pattern(nc, H.h_cell_p.data(), nv1, H.h_cell_p.data(), nv1, H.n_p, H.n_p_owned, H.n_p, H.hMp);
+  {
+    RowCells by_node, by_p; // the node -> cells and pressure DoF -> cells lists serve two patterns each
+    by_node.build(nc, H.h_cell_nodes.data(), n2, H.n_nodes);
+    build_pattern(by_node, H.h_cell_nodes.data(), n2, H.n_nodes_owned, H.n_nodes, H.hFs);
+    build_pattern(by_node, H.h_cell_p.data(), nv1, H.n_nodes, H.n_p, H.hBt);
+    by_p.build(nc, H.h_cell_p.data(), nv1, H.n_p);
+    build_pattern(by_p, H.h_cell_nodes.data(), n2, H.n_p_owned, H.n_nodes, H.hB);
+    build_pattern(by_p, H.h_cell_p.data(), nv1, H.n_p_owned, H.n_p, H.hMp);
+  }
   phase("sparsity patterns");
   symbolic_product(H.hB, H.hBt, H.hS);
   phase("symbolic Schur product");

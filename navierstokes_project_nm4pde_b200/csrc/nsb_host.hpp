@@ -61,8 +61,14 @@ struct Csr {
   int64_t nnz() const { return rowptr.empty() ? 0 : rowptr.back(); }
 };
 
+// cells adjacent to every row index (node or pressure DoF), cells ascending: shared by the patterns with the same rows
+struct RowCells {
+  std::vector<int> ptr, cells;
+  void build(int64_t nc, const int *cell_rows, int kr, int n_rows_total);
+};
 // rows r in [0, n_rows_owned): union over cells containing r of that cell's column entities.
 // cell_rows[nc][kr], cell_cols[nc][kc]; columns sorted ascending.
+void build_pattern(const RowCells &rc, const int *cell_cols, int kc, int n_rows_owned, int n_cols, Csr &out);
 void build_pattern(int64_t nc, const int *cell_rows, int kr, const int *cell_cols, int kc, int n_rows_total,
                    int n_rows_owned, int n_cols, Csr &out);
 // symbolic product pattern(A) * pattern(B), sorted columns
