@@ -18,7 +18,27 @@
 #include <cstring>
 #include <numeric>
 
+#include <sys/mman.h>
+
 namespace nsb {
+
+void prefault_parallel(void *p, size_t bytes)
+{
+#ifdef MADV_POPULATE_WRITE
+  const uintptr_t page = 4096, chunk = uintptr_t(32) << 20;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + page - 1) & ~(page - 1);
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(page - 1);
+  if (!p || bytes < (size_t(64) << 20) || e <= a) return;
+  const int64_t n = int64_t((e - a + chunk - 1) / chunk);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t i = 0; i < n; ++i) {
+    const uintptr_t b = a + uintptr_t(i) * chunk;
+    (void)madvise(reinterpret_cast<void *>(b), size_t(std::min(chunk, e - b)), MADV_POPULATE_WRITE); // a hint: failure is fine
+  }
+#else
+  (void)p; (void)bytes;
+#endif
+}
 
 void number_dofs(const Mesh &M, Dofs &D)
 {
@@ -127,6 +147,7 @@ void build_rows_chunked(int n_rows, Csr &out, GatherRow &&gather)
     }
   }
   for (int r = 0; r < n_rows; ++r) out.rowptr[r + 1] += out.rowptr[r];
+  reserve_prefaulted(out.colind, size_t(out.rowptr[n_rows]));
   out.colind.resize(size_t(out.rowptr[n_rows]));
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nchunks; ++ch) {

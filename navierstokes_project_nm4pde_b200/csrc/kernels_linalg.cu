@@ -955,6 +955,8 @@ static void permute_pattern(const Csr &A, const std::vector<int> &order, int n_o
   }
   if (missing_diag) throw StateError("ILU: structurally missing diagonal");
   for (int k = 0; k < n; ++k) rowptr[k + 1] += rowptr[k];
+  reserve_prefaulted(colind, size_t(rowptr[n]));
+  reserve_prefaulted(src, size_t(rowptr[n]));
   colind.assign(size_t(rowptr[n]), 0);
   src.assign(size_t(rowptr[n]), 0);
 #pragma omp parallel

@@ -269,7 +269,9 @@ extern "C" int nsb_set_quadrature(nsb_handle h, int32_t n_q, const double *xi, c
 template <typename T>
 static std::vector<T> interleave32(const std::vector<T> &in, int64_t nc, int64_t nc_pad, int k, T pad)
 { // [nc][k] -> [nc_pad/32][k][32]
-  std::vector<T> out(size_t(nc_pad) * k, pad);
+  std::vector<T> out;
+  reserve_prefaulted(out, size_t(nc_pad) * k);
+  out.assign(size_t(nc_pad) * k, pad);
 #pragma omp parallel for schedule(static)
   for (int64_t g = 0; g < nc_pad / 32; ++g) // one group of 32 cells = one contiguous piece of `out`
     for (int64_t c = g * 32; c < std::min(nc, g * 32 + 32); ++c)

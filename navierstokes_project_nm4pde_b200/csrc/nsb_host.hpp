@@ -55,6 +55,18 @@ void number_dofs(const Mesh &M, Dofs &D);
 // local P2 nodes (indices into the cell's n2 nodes) lying on local face f
 int face_local_nodes(int dim, int f, int out[6]);
 
+// Large host arrays: std::vector zero-fills on ONE thread, and for a fresh 1 GB allocation most of that time is the
+// kernel handing out zeroed pages.  reserve_prefaulted() reserves the storage and lets all host threads populate its
+// pages (madvise(MADV_POPULATE_WRITE): contents untouched), so the following resize() / assign() is a plain memset.
+void prefault_parallel(void *p, size_t bytes);
+template <typename T>
+inline void reserve_prefaulted(std::vector<T> &v, size_t n)
+{
+  v.clear();
+  v.reserve(n);
+  prefault_parallel(v.data(), n * sizeof(T));
+}
+
 struct Csr {
   int n_rows = 0, n_cols = 0;
   std::vector<int> rowptr, colind;
