@@ -52,6 +52,7 @@ void number_dofs(const Mesh &M, Dofs &D)
   struct ERec { int b, node, next; };
   std::vector<ERec> pool;
   pool.reserve(size_t(D.nc) * (dim == 2 ? 2 : 2));
+  reserve_prefaulted(D.cell_nodes, size_t(D.nc) * D.n2);
   D.cell_nodes.resize(size_t(D.nc) * D.n2);
   D.cell_p.resize(size_t(D.nc) * nv1);
   D.node_xyz.clear();
@@ -91,6 +92,8 @@ void number_dofs(const Mesh &M, Dofs &D)
   D.n_nodes = n_nodes;
   D.n_p = n_p;
   const int n_u = dim * n_nodes;
+  reserve_prefaulted(D.cell_dofs, size_t(D.nc) * D.dpc);
+  reserve_prefaulted(D.cell_coords, size_t(D.nc) * nv1 * dim);
   D.cell_dofs.resize(size_t(D.nc) * D.dpc);
   D.cell_coords.resize(size_t(D.nc) * nv1 * dim);
 #pragma omp parallel for schedule(static)

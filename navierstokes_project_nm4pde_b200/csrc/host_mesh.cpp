@@ -78,7 +78,9 @@ void Mesh::build_boundary(const std::function<int(const Mesh &, const int *)> &c
   }
   for (size_t i = 0; i < nv; ++i) start[i + 1] += start[i];
   struct Rec { int v1, v2; int64_t id; };
-  std::vector<Rec> recs(nf);
+  std::vector<Rec> recs;
+  reserve_prefaulted(recs, size_t(nf));
+  recs.resize(size_t(nf));
   {
     std::vector<int64_t> pos(start.begin(), start.end() - 1);
     for (int64_t id = 0; id < nf; ++id) { // face ids ascend inside every bucket
