@@ -231,6 +231,22 @@ def run_cpu(workload, steps, warmup, budget_s=None):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def pick_orderings(variant, n_dofs, world, ilu_ordering=-1, ilu_ordering_schur=-1):
+    """(ILU ordering of F_s, of the Schur complement) for the throughput mode; -1 = automatic.
+    F_s: by the DoFs one GPU holds -- block multicolour (2) above AUTO_BLOCK_MIN_DOFS, point multicolour (1) below
+    (measured: the block sweeps need large colours, profiles/README.md).
+    Schur complement: in 3D the pressure matrix keeps the point multicolour sweeps when F_s takes the block sweeps
+    (session M: 0.41 ms against 0.83 ms per apply at 19.9 M DoF, same CG iteration count).  In 2D (aSIMPLE: restarted
+    GMRES on the Schur complement, hundreds to thousands of iterations per solve) the block ordering, whose ILU(0) is as
+    good as the natural one -- with the point multicolour factors the inner GMRES hits the reference's 10 000-iteration
+    limit from 0.64 M DoF on (sessions M-P)."""
+    if ilu_ordering < 0:
+        ilu_ordering = 2 if n_dofs / max(world, 1) >= AUTO_BLOCK_MIN_DOFS else 1
+    if ilu_ordering_schur < 0:
+        ilu_ordering_schur = 2 if variant == "2d" else (1 if ilu_ordering == 2 else ilu_ordering)
+    return ilu_ordering, ilu_ordering_schur
+
+
 class GpuRun:
     """One problem instance on this rank's GPU, stepped through the host-buffer entry point."""
 
@@ -241,22 +257,9 @@ class GpuRun:
 
         self.torch = torch
         self.mesh, self.variant = make_mesh(workload)
-        if args.ilu_ordering < 0:  # automatic: by the DoFs one GPU holds
-            n_dofs = N_DOFS.get(workload) or HostDofsCount(self.mesh)
-            self.ilu_ordering = 2 if n_dofs / max(world, 1) >= AUTO_BLOCK_MIN_DOFS else 1
-        else:
-            self.ilu_ordering = args.ilu_ordering
-        # the pressure matrix keeps the point multicolour sweeps when F_s takes the block sweeps (session M: 0.41 ms
-        # against 0.83 ms per apply at 19.9 M DoF, same CG iteration count)
-        # 2D (aSIMPLE: restarted GMRES on the Schur complement, hundreds to thousands of iterations per solve): the block
-        # ordering, whose ILU(0) is as good as the natural one -- with the point multicolour factors the inner GMRES hits
-        # the reference's 10 000-iteration limit from 0.64 M DoF on (sessions M-P)
-        if args.ilu_ordering_schur >= 0:
-            self.ilu_ordering_schur = args.ilu_ordering_schur
-        elif self.variant == "2d":
-            self.ilu_ordering_schur = 2
-        else:
-            self.ilu_ordering_schur = 1 if self.ilu_ordering == 2 else self.ilu_ordering
+        n_dofs = N_DOFS.get(workload) or (HostDofsCount(self.mesh) if args.ilu_ordering < 0 else 0)
+        self.ilu_ordering, self.ilu_ordering_schur = pick_orderings(self.variant, n_dofs, world, args.ilu_ordering,
+                                                                    args.ilu_ordering_schur)
         self.dt = DELTAT[self.variant]
         kw = dict(T=1.0, deltat=self.dt, test_case=2, device=local_rank, ilu_ordering=self.ilu_ordering,
                   ilu_ordering_schur=self.ilu_ordering_schur, orthogonalisation=args.orthogonalisation)

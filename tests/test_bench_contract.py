@@ -170,3 +170,18 @@ def test_gpu_arm_on_two_ranks_over_gloo():
     assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["transport"] == "p2p" and "cpu_baseline" not in d
     assert 1 <= d["steps"] < 6 and d["detail"]["truncated"] is True  # extras 25 s + 0.8 s per slow step against 27.5 s
     assert d["ms_per_step"] == pytest.approx(800.0, rel=0.1)         # rank 1's time, not rank 0's 400 ms
+
+
+def test_ordering_selection_of_the_gpu_arm():
+    """What bench.py runs by default: block multicolour F_s + point multicolour Schur factors at 19.9 M DoF on one GPU,
+    point multicolour for both from two GPUs on, block-ordered Schur factors for the 2D family; explicit choices win."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    n = bench.N_DOFS["cyl3d-20M"]
+    assert bench.pick_orderings("3d", n, 1) == (2, 1)
+    assert [bench.pick_orderings("3d", n, w) for w in (2, 4, 8)] == [(1, 1)] * 3
+    assert bench.pick_orderings("3d", bench.N_DOFS["cyl3d-2M"], 1) == (1, 1)
+    assert bench.pick_orderings("2d", 1962041, 1) == (1, 2) and bench.pick_orderings("2d", 1962041, 2) == (1, 2)
+    assert bench.pick_orderings("3d", n, 1, 0, -1) == (0, 0) and bench.pick_orderings("3d", n, 1, 3, 1) == (3, 1)
+    assert bench.pick_orderings("3d", n, 8, 2, -1) == (2, 1)
